@@ -1,0 +1,133 @@
+/*
+ * fp4_b200.h — C-ABI of libfp4_b200.so: the B200 (sm_100a) implementation of the
+ * bitsandbytes-FP4 quantized nn.Linear hot path of aredden/torch-bnb-fp4.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and a CUDA stream handle (cudaStream_t passed as void*); no torch types.
+ * The reference binds the same operations through pybind11 in csrc/torch_fp4.cpp;
+ * each function below names the reference interface it replaces (file:line are
+ * relative to the reference repository).  The Python module `torch_bnb_fp4_ext`
+ * shipped in this repo is a thin binding over exactly these symbols.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless noted;
+ *   - `stream` is a cudaStream_t (0 = the legacy default stream); every call is
+ *     asynchronous on that stream, never synchronises, and is CUDA-graph capturable;
+ *   - return value: 0 on success, FP4_B200_ERR_* (<0) for rejected arguments,
+ *     or a positive cudaError_t for a launch failure.  Nothing is printed.
+ *   - packed layout (bitsandbytes `Params4bit.data`): element 2j is the HIGH nibble
+ *     of byte j, element 2j+1 the LOW nibble (reference csrc/dequant_fp4_optimized.cu:117-118);
+ *     quantisation blocks run over the FLATTENED [N*K] array, one fp32 absmax per
+ *     `blocksize` elements (reference :110).
+ *   - nibble -> value: the 16-entry fp32 codebook `code` (bitsandbytes QuantState.code);
+ *     passing code == NULL selects the bitsandbytes FP4 constants
+ *     {0, 0.0052083333, 0.66666667, 1, 0.33333333, 0.5, 0.16666667, 0.25} (and negatives for
+ *     nibble >= 8), which are the literals of the reference's tree decoder
+ *     (csrc/dequant_fp4_optimized.cu:55-76).
+ */
+#ifndef FP4_B200_H_
+#define FP4_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP4_B200_ABI_VERSION 1
+
+/* dtype codes (order matches the reference's ScalarTypeEnum, csrc/torch_fp4.cpp:22-26) */
+enum {
+    FP4_B200_F16 = 0,
+    FP4_B200_F32 = 1,
+    FP4_B200_BF16 = 2
+};
+
+/* status codes */
+enum {
+    FP4_B200_OK = 0,
+    FP4_B200_ERR_NULL = -1,       /* a required pointer is NULL                              */
+    FP4_B200_ERR_DTYPE = -2,      /* dtype code not one of FP4_B200_{F16,F32,BF16}            */
+    FP4_B200_ERR_SHAPE = -3,      /* negative / inconsistent sizes                            */
+    FP4_B200_ERR_BLOCKSIZE = -4,  /* blocksize not a power of two >= 2                        */
+    FP4_B200_ERR_ALIGN = -5,      /* pointer or row pitch not aligned as the kernel requires  */
+    FP4_B200_ERR_BATCH = -6,      /* gemv batch outside 1..8                                  */
+    FP4_B200_ERR_UNSUPPORTED = -7,/* shape outside what this entry point implements           */
+    FP4_B200_ERR_WORKSPACE = -8   /* workspace missing or too small                           */
+};
+
+/* flags for fp4_b200_gemv / fp4_b200_gemm */
+enum {
+    /* caller guarantees `code` (if non-NULL) holds the bitsandbytes FP4 constants bit for bit;
+       lets the GEMV use its integer tensor-core decode.  Without the flag a non-NULL code
+       is honoured entry by entry through the generic kernel. */
+    FP4_B200_FLAG_CODE_IS_BNB_FP4 = 1,
+    /* force the generic CUDA-core GEMV (testing / A-B timing) */
+    FP4_B200_FLAG_FORCE_GENERIC = 2
+};
+
+/* nested ("double-quantised") absmax, bitsandbytes QuantState.state2 + offset:
+ *   absmax_f32[i] = fp32_add(fp32_mul(code2[qabsmax[i]], absmax2[i / blocksize2]), offset)
+ * two separately rounded fp32 operations (no FMA).  SURVEY.md §8 N5. */
+typedef struct {
+    const uint8_t* qabsmax;  /* [nblocks] uint8 codes                         */
+    const float* code2;      /* [256] fp32 map (state2.code)                  */
+    const float* absmax2;    /* [ceil(nblocks / blocksize2)] fp32             */
+    float offset;            /* quant_state.offset                            */
+    int blocksize2;          /* state2.blocksize (256 in bitsandbytes)        */
+} fp4_b200_nested_t;
+
+int fp4_b200_abi_version(void);
+const char* fp4_b200_status_string(int status);
+
+/* Blockwise dequantise n elements:  out[i] = RN_T(fp32_mul(code[nib_i], absmax[i / blocksize])).
+ * Replaces dequantize_fp4 (csrc/torch_fp4.cpp:41-50 -> csrc/dequant_fp4_optimized.cu:182-205,
+ * tree kernel :89-123) when code == NULL, and dequantize_fp4_codebook (csrc/torch_fp4.cpp:52-62 ->
+ * csrc/dequant_fp4_optimized.cu:207-255) when code != NULL.
+ * packed: ceil(n/2) bytes, absmax: ceil(n/blocksize) floats, out: n elements of out_dtype.
+ * Requires: out 32-byte aligned, packed 8-byte aligned (torch allocations are 512-byte aligned). */
+int fp4_b200_dequantize(const uint8_t* packed, const float* absmax, const float* code,
+                        void* out, int64_t n, int blocksize, int out_dtype, void* stream);
+
+/* Same, with the absmax itself still double-quantised (decoded in the kernel, never materialised). */
+int fp4_b200_dequantize_nested(const uint8_t* packed, const fp4_b200_nested_t* nested,
+                               const float* code, void* out, int64_t n, int blocksize,
+                               int out_dtype, void* stream);
+
+/* Materialise a nested absmax to fp32 (load-time helper). */
+int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, int64_t nblocks,
+                           void* stream);
+
+/* Fused dequant + GEMV for decode:  out[b, r] = T( sum_k x[b,k] * code[W[r,k]] * absmax[(r*K+k)/blocksize] + bias[r] )
+ * for b < batch (1..8), r < N.  fp32 accumulation.  Replaces gemv_fp4 (csrc/torch_fp4.cpp:105-123 ->
+ * csrc/gemv_fp4_optimized.cu:277-368, kernels :60-259), which handles batch 1 only and adds the bias
+ * in a separate op (torch_bnb_fp4/__init__.py:608-613).
+ * x: [batch, K] dtype (row pitch K), out: [batch, N] dtype, bias: [N] dtype or NULL.
+ * Requires K % 32 == 0 (as the reference: 16-byte row chunks), blocksize % 32 == 0, K % blocksize == 0
+ * is NOT required (blocks may straddle rows as in bitsandbytes).
+ * nested may be NULL (absmax is fp32) or non-NULL (absmax ignored, decoded in the kernel). */
+int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
+                  const fp4_b200_nested_t* nested, const float* code, const void* bias, void* out,
+                  int batch, int N, int K, int blocksize, int dtype, unsigned flags, void* stream);
+
+/* Dequant-fused tensor-core GEMM for prefill:  out[m, r] = T( sum_k x[m,k] * W[r,k] + bias[r] ),
+ * W dequantised tile by tile in shared memory (never written to HBM) and multiplied with tcgen05.mma,
+ * fp32 accumulators in TMEM.  Replaces the reference's dequant + cuBLAS pair
+ * (torch_bnb_fp4/__init__.py:423-436; csrc/torch_fp4.cpp:64-103).
+ * dtype: FP4_B200_BF16 or FP4_B200_F16.  Requires K % 64 == 0, N % 8 == 0, blocksize % 64 == 0.
+ * workspace: reserved (may be NULL). */
+int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, const float* code,
+                  const void* bias, void* out, int M, int N, int K, int blocksize, int dtype,
+                  unsigned flags, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Blockwise FP4 quantiser with the bitsandbytes thresholds (kQuantizeBlockwise<FP4>; reached by the
+ * reference through bitsandbytes: torch_bnb_fp4/__init__.py:775).  w: n elements of dtype,
+ * packed: ceil(n/2) bytes, absmax: ceil(n/blocksize) floats. */
+int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
+                      float* absmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FP4_B200_H_ */

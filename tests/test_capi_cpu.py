@@ -1,0 +1,45 @@
+"""The C-ABI library loads and exports every symbol include/fp4_b200.h declares; argument
+validation that happens before any CUDA call is exercised (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "fp4_b200.h")).read()
+    return sorted(set(re.findall(r"\b(fp4_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = ctypes.CDLL(os.path.join(ROOT, "torch_bnb_fp4_b200", "libfp4_b200.so"))
+    names = _declared()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_binding_covers_header():
+    from torch_bnb_fp4_b200 import _lib
+
+    assert sorted(_lib.EXPORTS) == _declared()
+    assert _lib.lib.fp4_b200_abi_version() == 1
+
+
+def test_status_strings_and_early_validation():
+    from torch_bnb_fp4_b200._lib import lib
+
+    assert lib.fp4_b200_status_string(0) == b"ok"
+    assert b"NULL" in lib.fp4_b200_status_string(-1)
+    # rejected before any CUDA call
+    assert lib.fp4_b200_dequantize(None, None, None, None, 16, 64, 0, None) == -1
+    assert lib.fp4_b200_gemv(None, None, None, None, None, None, None, 1, 8, 64, 64, 0, 0, None) == -1
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 9, 8, 64, 64, 0, 0, None) == -6   # batch
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 48, 64, 0, 0, None) == -7   # K % 32
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 48, 0, 0, None) == -4   # blocksize
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 64, 7, 0, None) == -2   # dtype
+    assert lib.fp4_b200_quantize(None, 0, 16, 64, None, None, None) == -1
+    assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 48, 0, None) == -4
+    assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 64, 9, None) == -2
+    assert lib.fp4_b200_dequantize(1, 1, None, 1, 0, 64, 0, None) == 0                      # empty

@@ -1,0 +1,74 @@
+"""Host-side mirror of the reference interface: names, enum marshalling, error behaviour."""
+import pytest
+import torch
+
+import torch_bnb_fp4
+import torch_bnb_fp4_ext as ext
+from torch_bnb_fp4_b200 import bnb_compat
+
+
+def test_public_names_of_reference_module():
+    # reference torch_bnb_fp4/__init__.py:20-922
+    for name in ["ScalarType", "dequantize_fp4", "dequantize_fp4_codebook_invoke_qtype",
+                 "dequantize_fp4_codebook_invoke", "gemm_4bit_inference", "gemm_4bit_inference_qtype",
+                 "dequantize_fp4_qtype", "QuantData", "TorchFP4Linear", "swap_linear_with_bnb_linear",
+                 "check_if_name_contained_in_list", "todevice_if_necessary",
+                 "recursively_replace_with_fp4_linear", "T_Model"]:
+        assert hasattr(torch_bnb_fp4, name), name
+    assert hasattr(torch_bnb_fp4.TorchFP4Linear, "from_linear")
+
+
+def test_extension_names_of_reference_binding():
+    # reference csrc/torch_fp4.cpp:125-139 (+ .export_values())
+    for name in ["ScalarType", "bfloat16", "float16", "float32", "dequantize_fp4",
+                 "dequantize_fp4_codebook", "gemv_fp4", "qlinear", "qlinear_bias",
+                 "qlinear_codebook", "qlinear_codebook_bias"]:
+        assert hasattr(ext, name), name
+    assert ext.bfloat16 is ext.ScalarType.bfloat16
+
+
+def test_scalar_type_marshalling():
+    S = torch_bnb_fp4.ScalarType
+    assert S.from_torch_dtype(torch.bfloat16) is S.bfloat16
+    assert S.from_torch_dtype(torch.float16).value is ext.ScalarType.float16
+    assert S.from_str("float32") is S.float32
+    assert S.bfloat16.torch_dtype is torch.bfloat16
+    with pytest.raises(ValueError):
+        S.from_torch_dtype(torch.float64)
+    with pytest.raises(ValueError):
+        S.from_str("int8")
+    with pytest.raises(TypeError):
+        ext.get_scalar_type(17)
+
+
+def test_cpu_tensors_are_rejected_like_check_cuda():
+    A = torch.zeros(32, 1, dtype=torch.uint8)
+    am = torch.ones(1)
+    code = torch.tensor(ext.BNB_FP4_CODE)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.dequantize_fp4(A, am, 64, 8, 8, ext.float16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.dequantize_fp4_codebook(A, am, code, 8, 8, 64, 64, ext.bfloat16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.gemv_fp4(torch.zeros(1, 64), A, am, code, 64, ext.float32, [1, 64])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.qlinear(torch.zeros(2, 8), A, am, 8, 8, 64)
+    with pytest.raises(RuntimeError):
+        bnb_compat.BF.quantize_fp4(torch.randn(64, 64))  # no CPU quantiser
+
+
+def test_name_filter_and_dynamic_map():
+    assert torch_bnb_fp4.check_if_name_contained_in_list("model.lm_head", ["lm_head"])
+    assert not torch_bnb_fp4.check_if_name_contained_in_list("q_proj", ["lm_head"])
+    code = bnb_compat.create_dynamic_map()
+    assert code.numel() == 256 and torch.all(code[1:] >= code[:-1])
+    assert code.min() >= -1 and code.max() == 1.0
+    v = torch.randn(1000) * 0.01
+    q, am2 = bnb_compat.quantize_blockwise_8bit(v, code, 256)
+    rec = code[q.long()] * am2[torch.arange(1000) // 256]
+    assert (rec - v).abs().max() <= 0.06 * v.abs().max()
+
+
+def test_surgery_requires_cuda_device():
+    with pytest.raises(AssertionError):
+        torch_bnb_fp4.recursively_replace_with_fp4_linear(torch.nn.Linear(8, 8), device=torch.device("cpu"))

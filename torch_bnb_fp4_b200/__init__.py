@@ -1,0 +1,349 @@
+"""B200-native ``torch_bnb_fp4``: the reference's Python module surface (reference
+torch_bnb_fp4/__init__.py:20-922) over hand-written sm_100a kernels.
+
+Same public names, argument meaning and error behaviour as the reference for the quantised
+``nn.Linear`` forward path; the kernels underneath are new.  What differs on purpose:
+
+* ``QuantData.forward`` sends batch 1..8 inputs of any leading shape to the fused dequant-GEMV with
+  the bias added in the kernel epilogue (the reference: batch 1 only, bias as a second op,
+  :592-613), large inputs to the dequant-fused tcgen05 GEMM, everything else to dequant + cuBLAS;
+* the compute dtype follows each call's input (the reference latches the first call's dtype, :590-591);
+* nested (double-quantised) absmax is supported (the reference is not: README.md:223-224);
+* every kernel runs on the current stream and is CUDA-graph capturable.
+
+There is no CPU or PyTorch fallback for the kernels: importing this package without the built
+``libfp4_b200.so`` raises.
+"""
+from __future__ import annotations
+
+import logging
+from enum import Enum
+from math import prod
+from typing import List, Optional, Tuple, TypeVar, Union
+
+import torch
+from torch import nn
+
+from . import ext as _ext
+from ._lib import FLAG_FORCE_GENERIC  # noqa: F401
+from .bnb_compat import BF, HAVE_BNB, Linear4bit, LinearFP4, Params4bit  # noqa: F401
+from .ext import (dequantize_fp4 as dequantize_fp4_, dequantize_fp4_codebook as dequantize_fp4_codebook_,
+                  gemv_fp4 as gemv_fp4_, qlinear as qlinear_, qlinear_bias as qlinear_bias_,
+                  qlinear_codebook as qlinear_codebook_, qlinear_codebook_bias as qlinear_codebook_bias_)
+from .ext import ScalarType as ScalarType_
+
+T_Model = TypeVar("T_Model", bound=nn.Module)
+
+GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
+GEMM_MIN_ROWS = 64      # rows of x from which the dequant-fused tcgen05 GEMM is used (when built)
+
+
+class ScalarType(Enum):
+    """torch dtype <-> extension enum (reference torch_bnb_fp4/__init__.py:22-84)."""
+
+    bfloat16 = ScalarType_.bfloat16
+    float16 = ScalarType_.float16
+    float32 = ScalarType_.float32
+
+    @classmethod
+    def from_torch_dtype(cls, dtype: torch.dtype) -> "ScalarType":
+        if dtype == torch.bfloat16:
+            return cls.bfloat16
+        if dtype == torch.float16:
+            return cls.float16
+        if dtype == torch.float32:
+            return cls.float32
+        raise ValueError(f"Unsupported dtype {dtype}")
+
+    @classmethod
+    def from_str(cls, dtype: str) -> "ScalarType":
+        try:
+            return {"bfloat16": cls.bfloat16, "float16": cls.float16, "float32": cls.float32}[dtype]
+        except KeyError:
+            raise ValueError(f"Unsupported dtype {dtype}") from None
+
+    @property
+    def torch_dtype(self) -> torch.dtype:
+        # the reference's property names non-existent members (:77-82); this one works
+        return {ScalarType.bfloat16: torch.bfloat16, ScalarType.float16: torch.float16,
+                ScalarType.float32: torch.float32}[self]
+
+
+# ---- thin op shims (reference :87-337): same names, same argument order --------------------------
+@torch.no_grad()
+def dequantize_fp4(qweight, absmax, blocksize: int, M: int, N: int, dtype=torch.float16):
+    return dequantize_fp4_(qweight, absmax, blocksize, M, N, ScalarType.from_torch_dtype(dtype).value)
+
+
+@torch.no_grad()
+def dequantize_fp4_qtype(qweight, absmax, blocksize: int, M: int, N: int,
+                         dtype=ScalarType.bfloat16.value):
+    return dequantize_fp4_(qweight, absmax, blocksize, M, N, dtype)
+
+
+@torch.no_grad()
+def dequantize_fp4_codebook_invoke_qtype(qweight, absmax, code, blocksize: int, M: int, N: int,
+                                         numel: int, qtype):
+    return dequantize_fp4_codebook_(qweight, absmax, code, M, N, blocksize, numel, qtype)
+
+
+@torch.no_grad()
+def dequantize_fp4_codebook_invoke(qweight, absmax, code, blocksize: int, M: int, N: int,
+                                   numel: int, qtype: torch.dtype):
+    return dequantize_fp4_codebook_(qweight, absmax, code, M, N, blocksize, numel,
+                                    ScalarType.from_torch_dtype(qtype).value)
+
+
+@torch.no_grad()
+def gemm_4bit_inference(A, B, absmax, code, blocksize: int, dtype=torch.float16, Bshape=None):
+    return gemv_fp4_(A, B, absmax, code, blocksize, ScalarType.from_torch_dtype(dtype).value, Bshape)
+
+
+@torch.no_grad()
+def gemm_4bit_inference_qtype(A, B, absmax, code, blocksize: int,
+                              dtype=ScalarType.bfloat16.value, Bshape: List[int] = None):
+    return gemv_fp4_(A, B, absmax, code, blocksize, dtype, Bshape)
+
+
+class QuantData:
+    """Packed weight + quantisation state of one linear layer, and the forward dispatcher
+    (reference torch_bnb_fp4/__init__.py:340-618)."""
+
+    def __init__(self, A: torch.Tensor, state, shape: Tuple[int, int], original_lin,
+                 bias: Optional[torch.Tensor] = None, use_codebook_dequant: Optional[bool] = True,
+                 allow_reduced_precision_linear: Optional[bool] = False,
+                 materialize_nested_absmax: bool = False):
+        self.use_codebook_dequant = use_codebook_dequant
+        self.A = A
+        self.blocksize = state.blocksize
+        self.M = shape[0]  # out_features
+        self.N = shape[1]  # in_features
+        self.code = state.code.float().contiguous()
+        self.quant_state = state
+        self.original_lin = original_lin
+        self.numel = prod(shape)
+        self.nested = None
+        nblocks = (self.numel + self.blocksize - 1) // self.blocksize
+        if getattr(state, "nested", False):
+            # double-quantised absmax (reference: unsupported, README.md:223-224)
+            s2 = state.state2
+            offset = float(state.offset) if not torch.is_tensor(state.offset) else float(state.offset.item())
+            self.nested = _ext.make_nested(state.absmax.contiguous(), s2.code.float().contiguous(),
+                                           s2.absmax.float().contiguous(), offset, s2.blocksize)
+            self.absmax = None
+            if materialize_nested_absmax:
+                self.absmax = _ext.absmax_denest(self.nested, nblocks, A.device)
+                self.nested = None
+        else:
+            self.absmax = state.absmax.float().contiguous()
+        self.bias = original_lin.bias if hasattr(original_lin, "bias") else bias
+        self._bias_by_dtype = {}
+        self.o_type = None
+        self.qtype = None
+        self.compute_dtype_set = False
+        self.allow_reduced_precision_linear = allow_reduced_precision_linear
+        # the reference's "reduced precision" variants (:391-396) are the same dequant + linear done
+        # inside the extension; kept selectable, computed correctly
+        if allow_reduced_precision_linear and self.nested is None:
+            self.qlinear = (self._qlinear_low_precision_codebook if use_codebook_dequant
+                            else self._qlinear_low_precision_normal)
+        else:
+            self.qlinear = self._dequant_linear
+        self.dequantize = self._dequantize_codebook if use_codebook_dequant else self._dequantize_normal
+        self._code_is_std = _ext.code_is_bnb_fp4(self.code)  # one device->host read, at load time
+        self._Bshape = (self.M, self.N)
+
+    # -- dtype handling ---------------------------------------------------------------------------
+    def set_compute_type(self, x: torch.Tensor) -> None:
+        self.o_type = x.dtype
+        self.qtype = ScalarType.from_torch_dtype(x.dtype).value
+        if self.bias is not None:
+            b = self._bias_by_dtype.get(x.dtype)
+            if b is None:
+                b = self.bias.detach().to(dtype=x.dtype).contiguous()
+                self._bias_by_dtype[x.dtype] = b
+            self._bias_t = b
+        else:
+            self._bias_t = None
+        self.compute_dtype_set = True
+
+    # -- dequant ----------------------------------------------------------------------------------
+    def _dequantize_codebook(self) -> torch.Tensor:
+        if self.nested is not None:
+            return _ext.dequantize_fp4_nested(self.A, self.nested, self.code, self.M, self.N,
+                                              self.blocksize, self.qtype)
+        return dequantize_fp4_codebook_invoke_qtype(self.A, self.absmax, self.code, self.blocksize,
+                                                    self.M, self.N, self.numel, self.qtype)
+
+    def _dequantize_normal(self) -> torch.Tensor:
+        if self.nested is not None:
+            return _ext.dequantize_fp4_nested(self.A, self.nested, None, self.M, self.N,
+                                              self.blocksize, self.qtype)
+        return dequantize_fp4_qtype(self.A, self.absmax, self.blocksize, self.M, self.N, self.qtype)
+
+    def _dequant_linear(self, A: torch.Tensor) -> torch.Tensor:
+        return torch.nn.functional.linear(A, self.dequantize(), self._bias_t)
+
+    def _qlinear_low_precision_normal(self, A: torch.Tensor) -> torch.Tensor:
+        if self._bias_t is None:
+            return qlinear_(A, self.A, self.absmax, self.M, self.N, self.blocksize)
+        return qlinear_bias_(A, self.A, self.absmax, self.M, self.N, self.blocksize, self._bias_t)
+
+    def _qlinear_low_precision_codebook(self, A: torch.Tensor) -> torch.Tensor:
+        if self._bias_t is None:
+            return qlinear_codebook_(A, self.A, self.absmax, self.code, self.M, self.N, self.blocksize)
+        return qlinear_codebook_bias_(A, self.A, self.absmax, self.code, self.M, self.N,
+                                      self.blocksize, self._bias_t)
+
+    # -- fused paths ------------------------------------------------------------------------------
+    def _qgemv(self, A: torch.Tensor) -> torch.Tensor:
+        """Fused dequant-GEMV, bias in the epilogue.  A: [..., K] with <= 8 rows."""
+        return _ext.gemv_fp4_bias(A, self.A, self.absmax, self.code, self.blocksize, self.qtype,
+                                  self._Bshape, self._bias_t, self.nested)
+
+    def _qgemm(self, A: torch.Tensor) -> torch.Tensor:
+        return _ext.gemm_fp4(A, self.A, self.absmax, self.code, self.M, self.N, self.blocksize,
+                             self._bias_t)
+
+    def forward(self, A: torch.Tensor) -> torch.Tensor:
+        k = A.shape[-1]
+        n_el = A.numel()
+        if n_el == 0:  # same shapes as the reference's empty-input branch (:580-589)
+            B_shape = self.quant_state.shape
+            tail = B_shape[1:] if k == B_shape[0] else B_shape[:1]
+            return torch.empty(A.shape[:-1] + tail, dtype=A.dtype, device=A.device)
+        if A.dtype != self.o_type:
+            self.set_compute_type(A)
+        rows = n_el // k
+        if rows <= GEMV_MAX_BATCH and k % 32 == 0 and self.blocksize % 32 == 0:
+            if not A.is_contiguous():
+                A = A.contiguous()
+            return self._qgemv(A)
+        if (rows >= GEMM_MIN_ROWS and self.nested is None
+                and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype)):
+            if not A.is_contiguous():
+                A = A.contiguous()
+            return self._qgemm(A)
+        return self.qlinear(A)
+
+
+class TorchFP4Linear(nn.Module):
+    """Wrapper for a quantised bitsandbytes LinearFP4 / Linear4bit (reference :621-714)."""
+
+    def __init__(self, lin, use_codebook_dequant: bool = True, name: str = ""):
+        super().__init__()
+        self.lin = [lin]
+        self.in_features = lin.in_features
+        self.out_features = lin.out_features
+        self.use_codebook_dequant = use_codebook_dequant
+        self.name = name
+        w = lin.weight
+        if not (isinstance(w, Params4bit) or hasattr(w, "quant_state")):
+            raise ValueError("Linear is not a bnb linear and is not quantized, and I have no idea "
+                             "what to do with that rn.")
+        if (w.quant_state is None or w.device.type != "cuda" or w.data.dtype != torch.uint8):
+            raise ValueError("Linear weights are not quantized, and I have no idea what to do with "
+                             f"that rn. Weights are {w.data.dtype}")
+        qtype = getattr(w.quant_state, "quant_type", "fp4")
+        if qtype != "fp4":
+            raise ValueError(f"only quant_type='fp4' is supported, got {qtype!r}")
+        self.quant_data = QuantData(w.data, w.quant_state, w.quant_state.shape, bias=lin.bias,
+                                    original_lin=lin, use_codebook_dequant=use_codebook_dequant)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.quant_data.forward(x)
+
+    def __repr__(self) -> str:
+        lin = self.lin[0]
+        dt = f", dtype={self.quant_data.o_type}" if hasattr(self, "quant_data") else ""
+        return (f"TorchFP4Linear(in_features={lin.in_features}, out_features={lin.out_features}, "
+                f"bias={lin.bias is not None}{dt})")
+
+    @classmethod
+    def from_linear(cls, linear, use_codebook_dequant: bool = False, name: str = "") -> "TorchFP4Linear":
+        return cls(linear, use_codebook_dequant=use_codebook_dequant, name=name)
+
+
+@torch.no_grad()
+def swap_linear_with_bnb_linear(linear: nn.Linear, dtype=torch.float16):
+    """nn.Linear -> (unquantised) LinearFP4 carrying the same weights (reference :717-747)."""
+    mod = LinearFP4(linear.in_features, linear.out_features, bias=linear.bias is not None,
+                    compute_dtype=dtype)
+    mod.weight.data = linear.weight.data.clone().detach()
+    if linear.bias is not None:
+        mod.bias.data = linear.bias.data.clone().detach()
+    mod.requires_grad_(False)
+    return mod
+
+
+def check_if_name_contained_in_list(name, names_list):
+    return any(n in name for n in names_list)
+
+
+def todevice_if_necessary(module, device):
+    """Make sure a bnb linear is on `device` AND quantised (reference :759-778)."""
+    if module.weight.data.dtype != torch.uint8 and isinstance(module, (Linear4bit, LinearFP4)):
+        module.weight = module.weight.to(device)
+        if not (module.weight.data.device == torch.device(device)
+                and module.weight.data.dtype == torch.uint8):
+            logging.debug("layer reached the device unquantised; quantising it directly")
+            qweight, qstate = BF.quantize_fp4(module.weight.data)
+            module.weight.data = qweight
+            module.weight.quant_state = qstate
+    return module
+
+
+def _to_fp4(module, device, as_dtype, use_codebook_dequant, name):
+    if not isinstance(module, (LinearFP4, Linear4bit)):
+        module = swap_linear_with_bnb_linear(module, dtype=as_dtype)
+    module = module.to(device)
+    if getattr(module.weight, "quant_state", None) is None:
+        module = todevice_if_necessary(module, device)
+    return TorchFP4Linear(lin=module, use_codebook_dequant=use_codebook_dequant, name=name)
+
+
+def recursively_replace_with_fp4_linear(
+    module: T_Model, as_dtype=torch.float16, use_codebook_dequant=True,
+    device: torch.device = torch.device("cuda" if torch.cuda.is_available() else "cpu"),
+    return_final_module: bool = True, only_replace_bnb_layers: bool = False,
+    ignore_layer_names: List[str] = ["lm_head"], parent="", debug: bool = False,
+) -> Optional[T_Model]:
+    """Swap every nn.Linear / LinearFP4 / Linear4bit below `module` for a TorchFP4Linear
+    (reference :781-922; same keyword arguments and defaults)."""
+    dev_type = device.type if hasattr(device, "type") else str(device).split(":")[0]
+    assert dev_type == "cuda", "Device type must be cuda!"
+    prefix = parent + "." if parent != "" else ""
+    swapped_plain = False
+    for name, child in module.named_children():
+        child_name = prefix + name
+        if check_if_name_contained_in_list(name, ignore_layer_names):
+            if debug:
+                print(f"Ignoring name: {child_name}, as it is in the ignore list")
+            continue
+        if isinstance(child, (LinearFP4, Linear4bit)):
+            if debug:
+                print(f"Replacing BNB layer {child_name} swapping with TorchFP4Linear.")
+            module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant, child_name)
+        elif isinstance(child, nn.Linear):
+            if only_replace_bnb_layers:
+                if debug:
+                    print(f"Ignoring {child_name}, as only_replace_bnb_layers=True")
+            else:
+                if debug:
+                    print(f"Replacing {child_name} with BNB linear, and then swapping with TorchFP4Linear.")
+                module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant, child_name)
+                swapped_plain = True
+        elif isinstance(child, nn.Module):
+            recursively_replace_with_fp4_linear(
+                child, as_dtype=as_dtype, use_codebook_dequant=use_codebook_dequant, device=device,
+                return_final_module=False, only_replace_bnb_layers=only_replace_bnb_layers,
+                ignore_layer_names=ignore_layer_names, parent=child_name, debug=debug)
+    if isinstance(module, (LinearFP4, Linear4bit)):
+        module = _to_fp4(module, device, as_dtype, use_codebook_dequant, parent)
+    elif isinstance(module, nn.Linear) and not only_replace_bnb_layers:
+        module = _to_fp4(module, device, as_dtype, use_codebook_dequant, parent)
+        swapped_plain = True
+    if swapped_plain:
+        torch.cuda.empty_cache()
+    if return_final_module:
+        return module

@@ -1,0 +1,62 @@
+"""ctypes binding of libfp4_b200.so (the C-ABI in include/fp4_b200.h).  There is no fallback: if the
+library is missing or fails to load the import raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfp4_b200.so")
+
+F16, F32, BF16 = 0, 1, 2
+FLAG_CODE_IS_BNB_FP4 = 1
+FLAG_FORCE_GENERIC = 2
+
+EXPORTS = [
+    "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
+    "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv", "fp4_b200_gemm",
+    "fp4_b200_quantize",
+]
+
+
+class Nested(ctypes.Structure):
+    """fp4_b200_nested_t"""
+    _fields_ = [("qabsmax", ctypes.c_void_p), ("code2", ctypes.c_void_p),
+                ("absmax2", ctypes.c_void_p), ("offset", ctypes.c_float),
+                ("blocksize2", ctypes.c_int)]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m torch_bnb_fp4_b200.build` "
+            "(there is no CPU or PyTorch fallback for the FP4 kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
+    lib.fp4_b200_abi_version.restype = i32
+    lib.fp4_b200_status_string.restype = ctypes.c_char_p
+    lib.fp4_b200_status_string.argtypes = [i32]
+    lib.fp4_b200_dequantize.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.fp4_b200_dequantize_nested.argtypes = [vp, ctypes.POINTER(Nested), vp, vp, i64, i32, i32, vp]
+    lib.fp4_b200_absmax_denest.argtypes = [ctypes.POINTER(Nested), vp, i64, vp]
+    lib.fp4_b200_gemv.argtypes = [vp, vp, vp, ctypes.POINTER(Nested), vp, vp, vp, i32, i32, i32,
+                                  i32, i32, u32, vp]
+    lib.fp4_b200_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp,
+                                  ctypes.c_size_t, vp]
+    lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]
+    for name in EXPORTS:
+        getattr(lib, name)  # AttributeError if the ABI is incomplete
+        if name not in ("fp4_b200_status_string",):
+            getattr(lib, name).restype = i32
+    if lib.fp4_b200_abi_version() != 1:
+        raise ImportError("libfp4_b200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib.fp4_b200_status_string(status).decode()
+        raise RuntimeError(f"{what}: {msg} (status {status})")

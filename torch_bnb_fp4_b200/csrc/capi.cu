@@ -1,0 +1,115 @@
+// extern "C" surface of libfp4_b200.so (declared in include/fp4_b200.h): argument validation and
+// kernel selection only; the kernels live in dequant.cu, gemv_generic.cu, gemv_imma.cu, gemm_tcgen05.cu.
+#include "common.cuh"
+
+namespace fp4b200 {
+int dequant_dispatch(const uint8_t*, const float*, const fp4_b200_nested_t*, const float*, void*,
+                     int64_t, int, int, cudaStream_t);
+int denest_dispatch(const fp4_b200_nested_t*, float*, int64_t, cudaStream_t);
+int quantize_dispatch(const void*, int, int64_t, int, uint8_t*, float*, cudaStream_t);
+int gemv_generic_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*,
+                          const NestedDev&, const float*, const void*, void*, int, int, int, int,
+                          int, cudaStream_t);
+int gemv_imma_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*,
+                       const NestedDev&, const void*, void*, int, int, int, int, int,
+                       cudaStream_t);
+bool gemv_imma_supported(int batch, int N, int K, int blocksize, int dtype);
+int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float*, const void*,
+                          void*, int, int, int, int, int, unsigned, cudaStream_t);
+}  // namespace fp4b200
+
+using namespace fp4b200;
+
+extern "C" {
+
+int fp4_b200_abi_version(void) { return FP4_B200_ABI_VERSION; }
+
+const char* fp4_b200_status_string(int s) {
+    switch (s) {
+        case FP4_B200_OK: return "ok";
+        case FP4_B200_ERR_NULL: return "a required pointer is NULL";
+        case FP4_B200_ERR_DTYPE: return "unsupported dtype (expected float16, float32 or bfloat16)";
+        case FP4_B200_ERR_SHAPE: return "invalid shape";
+        case FP4_B200_ERR_BLOCKSIZE: return "blocksize must be a power of two";
+        case FP4_B200_ERR_ALIGN: return "pointer or row pitch is not sufficiently aligned";
+        case FP4_B200_ERR_BATCH: return "gemv batch must be in 1..8";
+        case FP4_B200_ERR_UNSUPPORTED: return "shape not supported by this entry point";
+        case FP4_B200_ERR_WORKSPACE: return "workspace missing or too small";
+        default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+    }
+}
+
+int fp4_b200_dequantize(const uint8_t* packed, const float* absmax, const float* code, void* out,
+                        int64_t n, int blocksize, int out_dtype, void* stream) {
+    if (!absmax) return FP4_B200_ERR_NULL;
+    return dequant_dispatch(packed, absmax, nullptr, code, out, n, blocksize, out_dtype,
+                            (cudaStream_t)stream);
+}
+
+int fp4_b200_dequantize_nested(const uint8_t* packed, const fp4_b200_nested_t* nested,
+                               const float* code, void* out, int64_t n, int blocksize,
+                               int out_dtype, void* stream) {
+    if (!nested) return FP4_B200_ERR_NULL;
+    return dequant_dispatch(packed, nullptr, nested, code, out, n, blocksize, out_dtype,
+                            (cudaStream_t)stream);
+}
+
+int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, int64_t nblocks,
+                           void* stream) {
+    return denest_dispatch(nested, absmax_out, nblocks, (cudaStream_t)stream);
+}
+
+int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
+                  const fp4_b200_nested_t* nested, const float* code, const void* bias, void* out,
+                  int batch, int N, int K, int blocksize, int dtype, unsigned flags,
+                  void* stream) {
+    if (!x || !packed || !out) return FP4_B200_ERR_NULL;
+    if (!nested && !absmax) return FP4_B200_ERR_NULL;
+    if (batch < 1 || batch > 8) return FP4_B200_ERR_BATCH;
+    if (N < 0 || K < 0) return FP4_B200_ERR_SHAPE;
+    if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16 && dtype != FP4_B200_F32)
+        return FP4_B200_ERR_DTYPE;
+    const int bs_log2 = ilog2_exact(blocksize);
+    if (bs_log2 < 0) return FP4_B200_ERR_BLOCKSIZE;
+    if (blocksize % 32 != 0) return FP4_B200_ERR_UNSUPPORTED;
+    if (K % 32 != 0) return FP4_B200_ERR_UNSUPPORTED;  // 16-byte row chunks, as the reference
+    if (N == 0) return FP4_B200_OK;
+    if (K == 0) return FP4_B200_ERR_SHAPE;
+    if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(x) % 16)
+        return FP4_B200_ERR_ALIGN;
+    NestedDev nd = {};
+    if (nested) {
+        if (!nested->qabsmax || !nested->code2 || !nested->absmax2) return FP4_B200_ERR_NULL;
+        const int l2 = ilog2_exact(nested->blocksize2);
+        if (l2 < 0) return FP4_B200_ERR_BLOCKSIZE;
+        nd = NestedDev{nested->qabsmax, nested->code2, nested->absmax2, nested->offset, l2};
+    }
+    const bool std_code = (code == nullptr) || (flags & FP4_B200_FLAG_CODE_IS_BNB_FP4);
+    if (std_code && !(flags & FP4_B200_FLAG_FORCE_GENERIC) &&
+        gemv_imma_supported(batch, N, K, blocksize, dtype))
+        return gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, batch, N, K, bs_log2,
+                                  dtype, (cudaStream_t)stream);
+    return gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
+                                 bs_log2, dtype, (cudaStream_t)stream);
+}
+
+int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, const float* code,
+                  const void* bias, void* out, int M, int N, int K, int blocksize, int dtype,
+                  unsigned flags, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    if (!x || !packed || !absmax || !out) return FP4_B200_ERR_NULL;
+    if (M < 0 || N < 0 || K <= 0) return FP4_B200_ERR_SHAPE;
+    if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16) return FP4_B200_ERR_DTYPE;
+    if (ilog2_exact(blocksize) < 0) return FP4_B200_ERR_BLOCKSIZE;
+    if (M == 0 || N == 0) return FP4_B200_OK;
+    return gemm_tcgen05_dispatch(x, packed, absmax, code, bias, out, M, N, K, blocksize, dtype,
+                                 flags, (cudaStream_t)stream);
+}
+
+int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
+                      float* absmax, void* stream) {
+    return quantize_dispatch(w, dtype, n, blocksize, packed, absmax, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+"""``torch_bnb_fp4_ext`` for B200: the reference's C++-extension op surface, same names, same
+positional signatures, same return shapes (reference csrc/torch_fp4.cpp:125-139), implemented as a
+thin binding over the C-ABI library ``libfp4_b200.so`` (include/fp4_b200.h).
+
+Differences from the reference binding, all deliberate:
+  * kernels launch on the CURRENT stream of the tensors' device (the reference uses the legacy
+    default stream with no device guard, csrc/gemv_fp4_optimized.cu:266), so every op is CUDA-graph
+    capturable; nothing synchronises;
+  * errors raise (RuntimeError / TypeError) instead of printing (csrc/dequant_fp4_optimized.cu:48-53,201-203);
+  * ``dequantize_fp4_codebook`` and ``gemv_fp4`` honour the ``code`` tensor they are handed (the
+    reference ignores it and uses its hard-coded CODE_PARAM, csrc/dequant_fp4_optimized.cu:207-255);
+  * ``gemv_fp4`` computes every row of A for batch 1..8 (the reference fills row 0 only, n=1 at
+    csrc/gemv_fp4_optimized.cu:289), accumulates in fp32, and ``gemv_fp4_bias`` fuses the bias;
+  * ``qlinear_codebook*`` dequantise the whole weight (the reference passes the byte count as the
+    element count and leaves half the matrix uninitialised, csrc/torch_fp4.cpp:90,101 — SURVEY N3).
+There is no CPU path: CPU tensors raise, exactly like the reference's CHECK_CUDA.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import weakref
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Nested, check, lib
+
+
+class ScalarType(enum.IntEnum):
+    """Mirror of the pybind enum (reference csrc/torch_fp4.cpp:22-26,126-130); values are the
+    C-ABI dtype codes."""
+    float16 = _lib.F16
+    float32 = _lib.F32
+    bfloat16 = _lib.BF16
+
+
+# .export_values() in the reference: the members are also module attributes
+float16 = ScalarType.float16
+float32 = ScalarType.float32
+bfloat16 = ScalarType.bfloat16
+
+_TORCH_DTYPE = {ScalarType.float16: torch.float16, ScalarType.float32: torch.float32,
+                ScalarType.bfloat16: torch.bfloat16}
+_CODE_OF = {torch.float16: _lib.F16, torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+BNB_FP4_CODE = (0.0, 5.208333333e-03, 0.66666667, 1.0, 0.33333333, 0.5, 0.16666667, 0.25,
+                -0.0, -5.208333333e-03, -0.66666667, -1.0, -0.33333333, -0.5, -0.16666667, -0.25)
+
+
+def get_scalar_type(t) -> torch.dtype:
+    """csrc/torch_fp4.cpp:28-39: bad enum -> TypeError."""
+    try:
+        return _TORCH_DTYPE[ScalarType(t)]
+    except (ValueError, KeyError, TypeError):
+        raise TypeError("Unsupported scalar type") from None
+
+
+def _check_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _check_contig(t: torch.Tensor, name: str) -> None:
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _check_in(t: torch.Tensor, name: str, dtype: Optional[torch.dtype] = None) -> None:
+    _check_cuda(t, name)
+    _check_contig(t, name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+class _on_device:
+    """Device guard + current stream of the tensor's device (c10::cuda::CUDAGuard equivalent)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index
+
+    def __enter__(self) -> int:
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return torch.cuda.current_stream(self.idx).cuda_stream
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+# ---- codebook identity cache ---------------------------------------------------------------------
+# The integer tensor-core GEMV is only valid for the bitsandbytes FP4 table.  Whether a given `code`
+# tensor holds it is checked ONCE per tensor object (one device->host read, outside the hot loop and
+# outside graph capture) and remembered while the tensor is alive and unmodified.
+_code_cache: dict = {}
+
+
+def code_is_bnb_fp4(code: torch.Tensor) -> bool:
+    key = id(code)
+    hit = _code_cache.get(key)
+    if hit is not None and hit[0]() is code and hit[1] == code._version:
+        return hit[2]
+    if torch.cuda.is_current_stream_capturing():
+        return False  # cannot read the table during capture: take the generic kernel
+    ref = torch.tensor(BNB_FP4_CODE, dtype=torch.float32)
+    ok = bool(code.numel() == 16 and code.dtype == torch.float32
+              and torch.equal(code.detach().float().cpu().view(torch.int32), ref.view(torch.int32)))
+    _code_cache[key] = (weakref.ref(code, lambda _r, k=key: _code_cache.pop(k, None)),
+                        code._version, ok)
+    return ok
+
+
+def make_nested(qabsmax: torch.Tensor, code2: torch.Tensor, absmax2: torch.Tensor, offset: float,
+                blocksize2: int) -> Nested:
+    """Pack a bitsandbytes nested state (state2 + offset) for the *_nested entry points."""
+    _check_in(qabsmax, "qabsmax", torch.uint8)
+    _check_in(code2, "code2", torch.float32)
+    _check_in(absmax2, "absmax2", torch.float32)
+    if code2.numel() != 256:
+        raise RuntimeError("nested code2 must have 256 entries")
+    n = Nested(qabsmax.data_ptr(), code2.data_ptr(), absmax2.data_ptr(), float(offset),
+               int(blocksize2))
+    n._keep = (qabsmax, code2, absmax2)  # keep the tensors alive as long as the struct
+    return n
+
+
+# ---- reference op surface --------------------------------------------------------------------------
+def dequantize_fp4(A: torch.Tensor, absmax: torch.Tensor, blocksize: int, M: int, N: int,
+                   o_type) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:41-50 (tree decoder == bitsandbytes constants)."""
+    _check_in(A, "A", torch.uint8)
+    _check_in(absmax, "absmax", torch.float32)
+    dt = get_scalar_type(o_type)
+    out = torch.empty((M, N), dtype=dt, device=A.device)
+    n = M * N
+    if A.numel() * 2 < n:
+        raise RuntimeError(f"A holds {A.numel()} bytes, fewer than M*N/2 = {n / 2}")
+    with _on_device(A) as st:
+        check(lib.fp4_b200_dequantize(A.data_ptr(), absmax.data_ptr(), None, out.data_ptr(), n,
+                                      blocksize, _CODE_OF[dt], st), "dequantize_fp4")
+    return out
+
+
+def dequantize_fp4_codebook(A: torch.Tensor, absmax: torch.Tensor, codebook: torch.Tensor, M: int,
+                            N: int, blocksize: int, n: int, dtype) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:52-62; `n` = number of ELEMENTS to dequantise (the tail of the
+    [M, N] output beyond n is left uninitialised, as in the reference)."""
+    _check_in(A, "A", torch.uint8)
+    _check_in(absmax, "absmax", torch.float32)
+    _check_in(codebook, "codebook", torch.float32)
+    if codebook.numel() != 16:
+        raise RuntimeError("codebook must have 16 entries")
+    dt = get_scalar_type(dtype)
+    if n < 0 or n > M * N or A.numel() * 2 < n:
+        raise RuntimeError(f"n={n} inconsistent with M*N={M * N} and {A.numel()} packed bytes")
+    out = torch.empty((M, N), dtype=dt, device=A.device)
+    with _on_device(A) as st:
+        check(lib.fp4_b200_dequantize(A.data_ptr(), absmax.data_ptr(), codebook.data_ptr(),
+                                      out.data_ptr(), n, blocksize, _CODE_OF[dt], st),
+              "dequantize_fp4_codebook")
+    return out
+
+
+def dequantize_fp4_nested(A: torch.Tensor, nested: Nested, codebook: Optional[torch.Tensor], M: int,
+                          N: int, blocksize: int, dtype) -> torch.Tensor:
+    """Extension: dequantise with a double-quantised absmax decoded in the kernel."""
+    _check_in(A, "A", torch.uint8)
+    dt = get_scalar_type(dtype)
+    out = torch.empty((M, N), dtype=dt, device=A.device)
+    with _on_device(A) as st:
+        check(lib.fp4_b200_dequantize_nested(
+            A.data_ptr(), ctypes.byref(nested), None if codebook is None else codebook.data_ptr(),
+            out.data_ptr(), M * N, blocksize, _CODE_OF[dt], st), "dequantize_fp4_nested")
+    return out
+
+
+def absmax_denest(nested: Nested, nblocks: int, device) -> torch.Tensor:
+    out = torch.empty(nblocks, dtype=torch.float32, device=device)
+    with _on_device(out) as st:
+        check(lib.fp4_b200_absmax_denest(ctypes.byref(nested), out.data_ptr(), nblocks, st),
+              "absmax_denest")
+    return out
+
+
+def _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags, what):
+    _check_in(A, "A")
+    _check_in(B, "B", torch.uint8)
+    if nested is None:
+        _check_in(absmax, "absmax", torch.float32)
+    if datatype is not None:
+        _check_in(datatype, "datatype", torch.float32)
+    dt = get_scalar_type(dtype)
+    if A.dtype != dt:
+        raise RuntimeError(f"A is {A.dtype} but dtype argument says {dt}")
+    n_out, k = int(Bshape[0]), int(Bshape[1])
+    if A.dim() not in (2, 3) or A.shape[-1] != k:
+        raise RuntimeError(f"A must be [batch, {k}] or [b0, b1, {k}], got {tuple(A.shape)}")
+    batch = A.numel() // k if k else 0
+    if B.numel() * 2 < n_out * k:
+        raise RuntimeError("B holds fewer than N*K/2 bytes")
+    if bias is not None:
+        _check_in(bias, "bias", dt)
+        if bias.numel() != n_out:
+            raise RuntimeError("bias must have N entries")
+    out = torch.empty(A.shape[:-1] + (n_out,), dtype=dt, device=A.device)
+    if batch == 0 or n_out == 0:
+        return out
+    if datatype is not None and code_is_bnb_fp4(datatype):
+        flags |= _lib.FLAG_CODE_IS_BNB_FP4
+    with _on_device(A) as st:
+        check(lib.fp4_b200_gemv(
+            A.data_ptr(), B.data_ptr(), None if absmax is None else absmax.data_ptr(),
+            None if nested is None else ctypes.byref(nested),
+            None if datatype is None else datatype.data_ptr(),
+            None if bias is None else bias.data_ptr(), out.data_ptr(), batch, n_out, k, blocksize,
+            _CODE_OF[dt], flags, st), what)
+    return out
+
+
+def gemv_fp4(A: torch.Tensor, B: torch.Tensor, absmax: torch.Tensor, datatype: torch.Tensor,
+             blocksize: int, dtype, Bshape: Sequence[int]) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:105-123 -> csrc/gemv_fp4_optimized.cu:277-368.
+    A: [batch, K] (or [b0, b1, K]) with batch <= 8; returns [batch, N] / [b0, b1, N]."""
+    return _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, None, None, 0, "gemv_fp4")
+
+
+def gemv_fp4_bias(A, B, absmax, datatype, blocksize, dtype, Bshape, bias=None, nested=None,
+                  flags: int = 0) -> torch.Tensor:
+    """Extension: bias fused in the epilogue (replaces the separate `out += bias`,
+    reference torch_bnb_fp4/__init__.py:608-613) and optional in-kernel nested absmax."""
+    return _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags,
+                 "gemv_fp4_bias")
+
+
+def gemm_fp4(A_in: torch.Tensor, A: torch.Tensor, absmax: torch.Tensor,
+             codebook: Optional[torch.Tensor], M: int, N: int, blocksize: int,
+             bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Extension: dequant-fused tcgen05 GEMM, y = A_in @ W[M, N]^T (+ bias).  bf16 / fp16 only."""
+    _check_in(A_in, "A_in")
+    _check_in(A, "A", torch.uint8)
+    _check_in(absmax, "absmax", torch.float32)
+    if A_in.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("gemm_fp4 supports float16 and bfloat16 inputs")
+    if A_in.shape[-1] != N:
+        raise RuntimeError(f"A_in last dim {A_in.shape[-1]} != in_features {N}")
+    rows = A_in.numel() // N if N else 0
+    out = torch.empty(A_in.shape[:-1] + (M,), dtype=A_in.dtype, device=A_in.device)
+    flags = 0
+    if codebook is not None:
+        _check_in(codebook, "codebook", torch.float32)
+        if code_is_bnb_fp4(codebook):
+            flags |= _lib.FLAG_CODE_IS_BNB_FP4
+    if bias is not None:
+        _check_in(bias, "bias", A_in.dtype)
+    with _on_device(A_in) as st:
+        check(lib.fp4_b200_gemm(
+            A_in.data_ptr(), A.data_ptr(), absmax.data_ptr(),
+            None if codebook is None else codebook.data_ptr(),
+            None if bias is None else bias.data_ptr(), out.data_ptr(), rows, M, N, blocksize,
+            _CODE_OF[A_in.dtype], flags, None, 0, st), "gemm_fp4")
+    return out
+
+
+def gemm_fp4_supported(rows: int, M: int, N: int, blocksize: int, dtype: torch.dtype) -> bool:
+    return (dtype in (torch.float16, torch.bfloat16) and N % 64 == 0 and M % 8 == 0
+            and blocksize % 64 == 0 and rows > 0 and GEMM_AVAILABLE)
+
+
+GEMM_AVAILABLE = False  # flipped by the package once the tcgen05 kernel is built in
+
+
+def _a_in_dtype(A_in: torch.Tensor) -> ScalarType:
+    try:
+        return ScalarType(_CODE_OF[A_in.dtype])
+    except KeyError:
+        raise RuntimeError(f"unsupported input dtype {A_in.dtype}") from None
+
+
+def qlinear(A_in: torch.Tensor, A: torch.Tensor, absmax: torch.Tensor, M: int, N: int,
+            blocksize: int) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:64-72: dequant (tree) to A_in's dtype, then linear."""
+    _check_cuda(A_in, "A_in")
+    w = dequantize_fp4(A, absmax, blocksize, M, N, _a_in_dtype(A_in))
+    return torch.nn.functional.linear(A_in, w)
+
+
+def qlinear_bias(A_in, A, absmax, M: int, N: int, blocksize: int, bias) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:74-82."""
+    _check_cuda(A_in, "A_in")
+    w = dequantize_fp4(A, absmax, blocksize, M, N, _a_in_dtype(A_in))
+    return torch.nn.functional.linear(A_in, w, bias)
+
+
+def qlinear_codebook(A_in, A, absmax, codebook, M: int, N: int, blocksize: int) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:84-92, with the whole weight dequantised."""
+    _check_cuda(A_in, "A_in")
+    w = dequantize_fp4_codebook(A, absmax, codebook, M, N, blocksize, M * N, _a_in_dtype(A_in))
+    return torch.nn.functional.linear(A_in, w)
+
+
+def qlinear_codebook_bias(A_in, A, absmax, codebook, M: int, N: int, blocksize: int,
+                          bias) -> torch.Tensor:
+    """reference csrc/torch_fp4.cpp:94-103, with the whole weight dequantised."""
+    _check_cuda(A_in, "A_in")
+    w = dequantize_fp4_codebook(A, absmax, codebook, M, N, blocksize, M * N, _a_in_dtype(A_in))
+    return torch.nn.functional.linear(A_in, w, bias)
+
+
+def quantize_fp4(w: torch.Tensor, blocksize: int = 64):
+    """Extension: CUDA FP4 quantiser with the bitsandbytes thresholds.  Returns
+    (packed uint8 [ceil(n/2), 1], absmax fp32 [ceil(n/blocksize)])."""
+    _check_in(w, "w")
+    if w.dtype not in _CODE_OF:
+        raise RuntimeError(f"unsupported dtype {w.dtype}")
+    n = w.numel()
+    packed = torch.empty(((n + 1) // 2, 1), dtype=torch.uint8, device=w.device)
+    absmax = torch.empty(((n + blocksize - 1) // blocksize,), dtype=torch.float32, device=w.device)
+    with _on_device(w) as st:
+        check(lib.fp4_b200_quantize(w.data_ptr(), _CODE_OF[w.dtype], n, blocksize,
+                                    packed.data_ptr(), absmax.data_ptr(), st), "quantize_fp4")
+    return packed, absmax
