@@ -144,15 +144,11 @@ def test_oracle_matches_reference_golden(path):
     packed, absmax = g["packed"], g["absmax"]
     for name, odt in (("f16", oracle.F16), ("bf16", oracle.BF16), ("f32", oracle.F32)):
         tree = oracle.dequant_tree(packed, absmax, n, bs, odt)
-        assert np.array_equal(tree.view(np.uint8), g[f"ref_tree_{name}"].view(np.uint8)), name
+        assert np.array_equal(tree.view(np.uint8), g[f"ref_tree_{name}"].ravel().view(np.uint8)), name
         # the reference's codebook op uses its own CODE_PARAM (it ignores the tensor it is given)
         cb = oracle.dequant_code(packed, absmax, oracle.ref_code_param(), n, bs, odt)
-        ref_cb = g[f"ref_codebook_{name}"]
-        if name == "f32":
-            # reference builds with --use_fast_math (FMUL.FTZ); inputs avoid fp32 denormals
-            assert np.array_equal(cb.view(np.uint8), ref_cb.view(np.uint8)), name
-        else:
-            assert np.array_equal(cb.view(np.uint8), ref_cb.view(np.uint8)), name
+        # (the reference builds with --use_fast_math => FMUL.FTZ; the fixtures avoid fp32 denormals)
+        assert np.array_equal(cb.view(np.uint8), g[f"ref_codebook_{name}"].ravel().view(np.uint8)), name
     # GEMV: tolerance (the reference's arithmetic is not IEEE-reproducible)
     N, K = int(g["N"]), int(g["K"])
     for name, odt in (("f16", oracle.F16), ("bf16", oracle.BF16), ("f32", oracle.F32)):
@@ -166,3 +162,6 @@ def test_oracle_matches_reference_golden(path):
         tol_exact = {"f16": 1e-2, "bf16": 5e-2, "f32": 1e-5}[name]   # real kernel vs fp64 truth
         assert np.max(np.abs(emu - ref_y)) / scale <= tol_emu, name
         assert np.max(np.abs(ref_y - exact)) / scale <= tol_exact, name
+        if name == "bf16":
+            # measured on B200: the N4 emulation reproduces the reference's bf16 GEMV bit for bit
+            assert np.array_equal(emu, ref_y)
