@@ -106,10 +106,18 @@ int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, i
  * x: [batch, K] dtype (row pitch K), out: [batch, N] dtype, bias: [N] dtype or NULL.
  * Requires K % 32 == 0 (as the reference: 16-byte row chunks), blocksize % 32 == 0, K % blocksize == 0
  * is NOT required (blocks may straddle rows as in bitsandbytes).
- * nested may be NULL (absmax is fp32) or non-NULL (absmax ignored, decoded in the kernel). */
+ * nested may be NULL (absmax is fp32) or non-NULL (absmax ignored, decoded in the kernel).
+ *
+ * workspace: device scratch of at least fp4_b200_gemv_workspace_bytes(N) bytes, 256-byte aligned,
+ * ZERO-FILLED once by the caller before its first use (the kernel keeps its counters zero between
+ * launches) and not shared by launches that may run concurrently (one per stream).  It holds the
+ * partial sums of row tiles that the stream-K schedule splits between warps.  Passing NULL selects
+ * the generic CUDA-core kernel, which needs none. */
 int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                   const fp4_b200_nested_t* nested, const float* code, const void* bias, void* out,
-                  int batch, int N, int K, int blocksize, int dtype, unsigned flags, void* stream);
+                  int batch, int N, int K, int blocksize, int dtype, unsigned flags,
+                  void* workspace, size_t workspace_bytes, void* stream);
+size_t fp4_b200_gemv_workspace_bytes(int N);
 
 /* Dequant-fused tensor-core GEMM for prefill:  out[m, r] = T( sum_k x[m,k] * W[r,k] + bias[r] ),
  * W dequantised tile by tile in shared memory (never written to HBM) and multiplied with tcgen05.mma,

@@ -34,11 +34,13 @@ def test_status_strings_and_early_validation():
     assert b"NULL" in lib.fp4_b200_status_string(-1)
     # rejected before any CUDA call
     assert lib.fp4_b200_dequantize(None, None, None, None, 16, 64, 0, None) == -1
-    assert lib.fp4_b200_gemv(None, None, None, None, None, None, None, 1, 8, 64, 64, 0, 0, None) == -1
-    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 9, 8, 64, 64, 0, 0, None) == -6   # batch
-    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 48, 64, 0, 0, None) == -7   # K % 32
-    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 48, 0, 0, None) == -4   # blocksize
-    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 64, 7, 0, None) == -2   # dtype
+    assert lib.fp4_b200_gemv(None, None, None, None, None, None, None, 1, 8, 64, 64, 0, 0, None, 0, None) == -1
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 9, 8, 64, 64, 0, 0, None, 0, None) == -6   # batch
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 48, 64, 0, 0, None, 0, None) == -7   # K % 32
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 48, 0, 0, None, 0, None) == -4   # blocksize
+    assert lib.fp4_b200_gemv(1, 1, 1, None, None, None, 1, 1, 8, 64, 64, 7, 0, None, 0, None) == -2   # dtype
+    assert lib.fp4_b200_gemv(16, 16, 16, None, None, None, 16, 1, 16, 64, 64, 0, 0, 256, 8, None) == -8  # workspace too small
+    assert lib.fp4_b200_gemv_workspace_bytes(4096) >= 4096 // 16 * 4
     assert lib.fp4_b200_quantize(None, 0, 16, 64, None, None, None) == -1
     assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 48, 0, None) == -4
     assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 64, 9, None) == -2

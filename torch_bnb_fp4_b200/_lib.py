@@ -14,7 +14,8 @@ FLAG_FORCE_GENERIC = 2
 
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
-    "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv", "fp4_b200_gemm",
+    "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
+    "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemm",
     "fp4_b200_quantize",
 ]
 
@@ -40,14 +41,16 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_dequantize_nested.argtypes = [vp, ctypes.POINTER(Nested), vp, vp, i64, i32, i32, vp]
     lib.fp4_b200_absmax_denest.argtypes = [ctypes.POINTER(Nested), vp, i64, vp]
     lib.fp4_b200_gemv.argtypes = [vp, vp, vp, ctypes.POINTER(Nested), vp, vp, vp, i32, i32, i32,
-                                  i32, i32, u32, vp]
+                                  i32, i32, u32, vp, ctypes.c_size_t, vp]
+    lib.fp4_b200_gemv_workspace_bytes.argtypes = [i32]
     lib.fp4_b200_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp,
                                   ctypes.c_size_t, vp]
     lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the ABI is incomplete
-        if name not in ("fp4_b200_status_string",):
+        if name not in ("fp4_b200_status_string", "fp4_b200_gemv_workspace_bytes"):
             getattr(lib, name).restype = i32
+    lib.fp4_b200_gemv_workspace_bytes.restype = ctypes.c_size_t
     if lib.fp4_b200_abi_version() != 1:
         raise ImportError("libfp4_b200.so ABI version mismatch")
     return lib

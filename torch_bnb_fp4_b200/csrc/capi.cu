@@ -11,9 +11,10 @@ int gemv_generic_dispatch(const void*, const uint8_t*, const float*, const fp4_b
                           const NestedDev&, const float*, const void*, void*, int, int, int, int,
                           int, cudaStream_t);
 int gemv_imma_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*,
-                       const NestedDev&, const void*, void*, int, int, int, int, int,
+                       const NestedDev&, const void*, void*, void*, size_t, int, int, int, int, int,
                        cudaStream_t);
 bool gemv_imma_supported(int batch, int N, int K, int blocksize, int dtype);
+size_t gemv_imma_workspace_bytes(int N);
 int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float*, const void*,
                           void*, int, int, int, int, int, unsigned, cudaStream_t);
 }  // namespace fp4b200
@@ -62,7 +63,7 @@ int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, i
 int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                   const fp4_b200_nested_t* nested, const float* code, const void* bias, void* out,
                   int batch, int N, int K, int blocksize, int dtype, unsigned flags,
-                  void* stream) {
+                  void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !packed || !out) return FP4_B200_ERR_NULL;
     if (!nested && !absmax) return FP4_B200_ERR_NULL;
     if (batch < 1 || batch > 8) return FP4_B200_ERR_BATCH;
@@ -85,13 +86,18 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
         nd = NestedDev{nested->qabsmax, nested->code2, nested->absmax2, nested->offset, l2};
     }
     const bool std_code = (code == nullptr) || (flags & FP4_B200_FLAG_CODE_IS_BNB_FP4);
-    if (std_code && !(flags & FP4_B200_FLAG_FORCE_GENERIC) &&
-        gemv_imma_supported(batch, N, K, blocksize, dtype))
-        return gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, batch, N, K, bs_log2,
-                                  dtype, (cudaStream_t)stream);
+    if (std_code && !(flags & FP4_B200_FLAG_FORCE_GENERIC) && workspace &&
+        gemv_imma_supported(batch, N, K, blocksize, dtype)) {
+        if (workspace_bytes < gemv_imma_workspace_bytes(N)) return FP4_B200_ERR_WORKSPACE;
+        return gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, workspace,
+                                  workspace_bytes, batch, N, K, bs_log2, dtype,
+                                  (cudaStream_t)stream);
+    }
     return gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
                                  bs_log2, dtype, (cudaStream_t)stream);
 }
+
+size_t fp4_b200_gemv_workspace_bytes(int N) { return N > 0 ? gemv_imma_workspace_bytes(N) : 0; }
 
 int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, const float* code,
                   const void* bias, void* out, int M, int N, int K, int blocksize, int dtype,

@@ -110,6 +110,12 @@ __device__ __forceinline__ float load_absmax(const float* absmax, const NestedDe
     }
 }
 
+// GEMV workspace: per-row-tile unit counters first (must be zero before the first launch; the kernel
+// leaves them zero), then the fp32 partial-sum slots.
+static inline size_t fp4b200_ws_counter_bytes(int N) {
+    return (((size_t)(N + 15) / 16) * 4 + 255) & ~(size_t)255;
+}
+
 static inline int ilog2_exact(int64_t v) {  // -1 if v is not a power of two
     if (v <= 0 || (v & (v - 1))) return -1;
     int l = 0;

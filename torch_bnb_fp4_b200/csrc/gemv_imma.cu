@@ -2,9 +2,9 @@
 //
 // Replaces gemv_4bit_inference_kernel{,_float} (reference csrc/gemv_fp4_optimized.cu:60-259).
 // Bound: HBM.  Algorithmic bytes per weight: 0.5 (packed) + 4/blocksize (absmax) = 0.5625 at
-// blocksize 64.  At the measured 6.56 TB/s one SM must retire ~41 weights per clock, which leaves
-// ~3 issue slots per weight in total; a per-nibble shared-memory lookup + FFMA (the reference's
-// scheme: 32 LDS + 32 HMUL2 + 32 HFMA2 per 16 bytes) does not fit.  This kernel therefore
+// blocksize 64.  At the measured 6.56 TB/s one SM must retire ~41 weights per clock, i.e. ~4 warp
+// instructions per 32 weights in total; a per-nibble shared-memory lookup + FMA (the reference's
+// scheme: 32 LDS + 32 HMUL2 + 32 HFMA2 per 16 bytes) cannot fit.  This kernel therefore
 //   * decodes FOUR nibbles per instruction with PRMT used as an 8-entry byte table: the
 //     bitsandbytes FP4 magnitudes times 12 are {0, 1/16, 8, 12, 4, 6, 2, 3} - exactly representable
 //     in e5m2, i.e. one byte each, the high byte of their fp16 encoding;
@@ -12,24 +12,29 @@
 //   * widens e5m2 -> fp16 with F2FP (cvt.rn.f16x2.e5m2x2: the byte becomes the high byte, exact);
 //   * feeds the fp16 pairs to mma.sync.m16n8k16 (fp32 accumulate) as the A operand: 16 weight rows x
 //     16 k per instruction, B = x (8 columns = up to 8 batch rows, so batch 2..8 costs no extra
-//     decode work).  This is not a reshaping of the problem into a GEMM: it is the same contraction,
-//     with the multiply-adds moved off the issue-limited FMA pipe.
+//     decode work).  The contraction is unchanged; the multiply-adds just leave the FMA pipe.
 // The absmax is factored out of the inner sum, y[r] = sum_b absmax[r,b] * sum_{k in b} c12[q]*x[k],
 // so products are exact (fp16 x fp16 in fp32) and each 64-element block costs 4 FFMA per lane.
 // x is staged ONCE per CTA in shared memory as fp16, pre-scaled by a power of two per batch row so
 // that bf16/fp32 inputs cannot overflow fp16 (fp32 inputs are split hi + lo into two columns, ~22
 // bits), and stored in mma B-fragment order so a lane fetches its operands with two LDS.128 per
-// block.  Weights stream with 64-bit ld.global.nc.L1::no_allocate loads, U blocks in flight per lane
-// (each warp instruction reads whole 32-byte sectors of 8 rows; a warp's U consecutive loads cover
-// whole 128-byte lines), issued before the x staging so the first HBM round trip is overlapped.
+// block.  Weights stream with 64-bit ld.global.nc.L1::no_allocate loads, kU blocks in flight per
+// lane and row (a warp instruction reads whole 32-byte sectors of 8 rows; kU consecutive loads cover
+// whole 128-byte lines); the first loads are issued before the x staging to overlap the first HBM
+// round trip.
 //
-// Grid: one CTA of 8 warps covers 16*RW rows x all K, warps arranged RW (row tiles) x KW (k split),
-// partial sums combined through shared memory; RW/KW are chosen per shape so that small layers still
-// put >= ~2 CTAs on each of the 148 SMs.
+// Schedule ("stream-K"): the work is the flat sequence of units (row tile of 16 rows, 64-wide k
+// block), 1 KiB of packed weights each.  The grid is persistent - (CTAs per SM) x 148 CTAs of 8
+// warps - and every WARP owns an equal contiguous range of units (+-1), so there is no wave
+// quantisation whatever N and K are, and x is staged once per CTA instead of once per row tile.
+// A warp that covers a row tile alone writes the output directly; tiles shared between warps are
+// combined deterministically: each contributor stores its fp32 partial in a workspace slot, bumps a
+// per-tile counter, and the last arriver sums the slots in warp order, applies scale and bias,
+// converts and stores (and resets the counter for the next launch).
 //
 // Requirements (checked by gemv_imma_supported): codebook == bitsandbytes FP4 table, K % 64 == 0,
-// blocksize % 64 == 0, N % 16 == 0, shared memory for x <= 200 KB.  Everything else takes
-// gemv_generic.cu.
+// blocksize % 64 == 0, N % 16 == 0, shared memory for x <= 200 KB, a workspace.  Everything else
+// takes gemv_generic.cu.
 #include "common.cuh"
 
 #include <cstdlib>
@@ -38,7 +43,10 @@ namespace fp4b200 {
 
 namespace {
 
-constexpr int kU = 4;  // 64-element blocks in flight per lane (per row)
+constexpr int kU = 4;        // units in flight per lane (per row)
+constexpr int kWarps = 8;    // warps per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr size_t kCounterBytes = 256 * 1024;  // fixed-size counter region: 65536 row tiles (N <= 2^20)
 
 // e5m2 bytes (= high byte of fp16) of 12*|code[i]|, i = 0..7: 0, 1/16, 8, 12 | 4, 6, 2, 3
 constexpr uint32_t kTabLo = 0x4A482C00u;
@@ -124,147 +132,240 @@ __device__ __forceinline__ uint4 pack_swapped(const float (&v)[8]) {
     return r;
 }
 
+// Balanced flat partition of B units over W warps: the first r = B % W warps get q+1 units.
+struct Partition {
+    uint32_t q, r;
+    __device__ __forceinline__ uint32_t begin(uint32_t w) const { return w * q + (w < r ? w : r); }
+    __device__ __forceinline__ uint32_t owner(uint32_t u) const {  // warp whose range holds unit u
+        const uint32_t big = r * (q + 1);
+        return u < big ? u / (q + 1) : r + (u - big) / q;
+    }
+};
+
+struct Workspace {
+    unsigned* counters;  // [kMaxTiles] units accounted for per row tile; zero between launches
+    float* partials;     // [W][2][16][NC] fp32
+};
+
 // T: activation dtype.  PIECES = 1 (fp16/bf16 x: one fp16 column per batch row) or 2 (fp32 x: hi + lo).
 // NCOLT = number of 8-column MMA tiles (1, or 2 when batch*PIECES > 8).
 template <typename T, int NCOLT, bool NESTED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kThreads)
 gemv_mma_kernel(const T* __restrict__ x, const uint8_t* __restrict__ packed,
                 const float* __restrict__ absmax, const NestedDev nd, const T* __restrict__ bias,
-                T* __restrict__ out, const int batch, const int N, const int K, const int bs_log2,
-                const int kw_log2) {
+                T* __restrict__ out, const Workspace ws, const int batch, const int N, const int K,
+                const int am_shift /* log2(blocksize / 64) */) {
     constexpr int PIECES = (sizeof(T) == 4) ? 2 : 1;
+    constexpr int NC = 8 * NCOLT;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int nkb = K >> 6;
+    __shared__ float sPart[kWarps][2][16][NC];  // CTA-local partial sums of shared row tiles
+    __shared__ unsigned sCnt[kWarps];           // units accounted for, by first contributing warp
+    __shared__ float sMax[kWarps * 8];
+    __shared__ float sScale[8];
+    const uint32_t nkb = (uint32_t)K >> 6;
     const int ncols = batch * PIECES;
-    uint4* sB = reinterpret_cast<uint4*>(smem_raw);                  // [nkb][2][ncols][4] x 16 B
-    float* sRed = reinterpret_cast<float*>(sB + (size_t)nkb * 2 * ncols * 4);  // [8][16][8*NCOLT]
-    float* sMax = sRed + 8 * 16 * 8 * NCOLT;                         // [8 warps][8 batch]
-    float* sScale = sMax + 64;                                       // [8 batch] inverse scales
+    uint4* sB = reinterpret_cast<uint4*>(smem_raw);  // [nkb][2][ncols][4] x 16 B
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int KW = 1 << kw_log2, RW = 8 >> kw_log2;
-    const int rt = warp >> kw_log2, kwi = warp & (KW - 1);
-    const int rowbase = (blockIdx.x * RW + rt) * 16;
-    const bool tile_valid = rowbase < N;
-    const int r0 = tile_valid ? rowbase + g : g;  // clamp: loads stay in bounds, results unused
-    const int r1 = r0 + 8;
-    const int per = (nkb + KW - 1) >> kw_log2;
-    const int kb_begin = kwi * per;
-    const int kb_end = (kb_begin + per < nkb) ? kb_begin + per : nkb;
+    const uint32_t g = lane >> 2, t = lane & 3;
 
-    const uint8_t* p0 = packed + (((int64_t)r0 * K) >> 1) + 8 * t;
-    const uint8_t* p1 = packed + (((int64_t)r1 * K) >> 1) + 8 * t;
-    const int64_t e0 = (int64_t)r0 * K, e1 = (int64_t)r1 * K;
+    const uint32_t ntiles = (uint32_t)N >> 4;
+    const uint32_t B = ntiles * nkb;
+    const uint32_t W = gridDim.x * kWarps;
+    const Partition part{B / W, B % W};
+    const uint32_t wid = blockIdx.x * kWarps + warp;
+    const uint32_t L0 = part.begin(wid), L1 = part.begin(wid + 1);
+    const uint32_t n = L1 - L0;
+    const uint32_t cta_L0 = part.begin(blockIdx.x * kWarps), cta_L1 = part.begin((blockIdx.x + 1) * kWarps);
+    if (tid < kWarps) sCnt[tid] = 0;
 
-    // ---- 1. put the first U blocks of the weight stream in flight ------------------------------
+    // ---- load cursor: unit L -> (tile, kb); offsets advance by constant steps with a wrap -------
+    // index in 64-element units of (row tile*16+g, kb): (tile*16+g)*nkb + kb; the packed bytes sit at
+    // 32 x that (+ 8t), the absmax at that >> am_shift
+    uint32_t ld_kb = n ? L0 % nkb : 0;
+    uint32_t ld_u64 = n ? ((L0 / nkb) * 16 + g) * nkb + ld_kb : 0;
+    const uint32_t wrap_u64 = 15 * nkb + 1;  // from the last block of a tile to block 0 of the next
+    const uint8_t* wp = packed + 8 * t;
+    const uint32_t r8 = 8 * nkb;             // +8 rows, in 64-element units
+
     uint2 q0[kU], q1[kU];
     float a0[kU], a1[kU];
+    auto issue_load = [&](int u) {
+        q0[u] = ldg_stream_u2(wp + (size_t)ld_u64 * 32);
+        q1[u] = ldg_stream_u2(wp + (size_t)(ld_u64 + r8) * 32);
+        a0[u] = load_absmax<NESTED>(absmax, nd, (int64_t)(ld_u64 >> am_shift));
+        a1[u] = load_absmax<NESTED>(absmax, nd, (int64_t)((ld_u64 + r8) >> am_shift));
+        const bool wrap = (++ld_kb == nkb);
+        ld_u64 += wrap ? wrap_u64 : 1u;
+        if (wrap) ld_kb = 0;
+    };
+    // ---- 1. put the first kU units of the weight stream in flight ------------------------------
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-        const int kb = kb_begin + u;
-        if (kb < kb_end) {
-            q0[u] = ldg_stream_u2(p0 + kb * 32);
-            q1[u] = ldg_stream_u2(p1 + kb * 32);
-            a0[u] = load_absmax<NESTED>(absmax, nd, (e0 + (int64_t)kb * 64) >> bs_log2);
-            a1[u] = load_absmax<NESTED>(absmax, nd, (e1 + (int64_t)kb * 64) >> bs_log2);
-        }
-    }
+    for (int u = 0; u < kU; ++u)
+        if ((uint32_t)u < n) issue_load(u);
 
-    // ---- 2. stage x as scaled fp16 in B-fragment order -----------------------------------------
+    // ---- 2. stage x as scaled fp16 in B-fragment order (once per CTA) --------------------------
     const int nchunk = K >> 3;  // 8-element chunks per batch row
-    {   // pass 1: max |x| per batch row
-        float mx[8];
+    for (int b = 0; b < batch; ++b) {  // pass 1: max |x| per batch row
+        float mx = 0.f;
+        for (int c = tid; c < nchunk; c += kThreads) {
+            float f[8];
+            XLoad<T>::load(x + (size_t)b * K + c * 8, f);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) mx[b] = 0.f;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if (b < batch) {
-                for (int c = tid; c < nchunk; c += 256) {
-                    float f[8];
-                    XLoad<T>::load(x + (int64_t)b * K + c * 8, f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) mx[b] = fmaxf(mx[b], fabsf(f[i]));
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    mx[b] = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], o));
-                if (lane == 0) sMax[warp * 8 + b] = mx[b];
-            }
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[i]));
         }
-        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) sMax[warp * 8 + b] = mx;
     }
-    float scale[8];  // power of two bringing max|x| into [2^13, 2^14)
+    __syncthreads();
+    for (int b = 0; b < batch; ++b) {  // pass 2: scale into [2^13, 2^14), convert, store
+        float m = 0.f;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        scale[b] = 0.f;
-        if (b < batch) {
-            float m = 0.f;
+        for (int w = 0; w < kWarps; ++w) m = fmaxf(m, sMax[w * 8 + b]);
+        int E = (int)((__float_as_uint(m) >> 23) & 0xFFu);
+        E = E < 14 ? 14 : (E > 254 ? 254 : E);
+        const float scale = __uint_as_float((uint32_t)(267 - E) << 23);  // 2^(13 - e)
+        if (tid == 0) sScale[b] = __uint_as_float((uint32_t)(E - 13) << 23) * (1.f / 12.f);
+        for (int c = tid; c < nchunk; c += kThreads) {
+            float f[8];
+            XLoad<T>::load(x + (size_t)b * K + c * 8, f);
 #pragma unroll
-            for (int w = 0; w < 8; ++w) m = fmaxf(m, sMax[w * 8 + b]);
-            int E = (int)((__float_as_uint(m) >> 23) & 0xFFu);
-            E = E < 14 ? 14 : (E > 254 ? 254 : E);
-            scale[b] = __uint_as_float((uint32_t)(267 - E) << 23);
-            if (tid == 0) sScale[b] = __uint_as_float((uint32_t)(E - 13) << 23);  // 2^-(13-e)
-        }
-    }
+            for (int i = 0; i < 8; ++i) f[i] *= scale;
+            const int kb = c >> 3, qq = c & 7;  // chunk qq of the block: lane t = qq/2, half = qq%2
+            uint4* dst = sB + ((size_t)(kb * 2 + (qq & 1)) * ncols + b * PIECES) * 4 + (qq >> 1);
+            dst[0] = pack_swapped(f);
+            if constexpr (PIECES == 2) {
+                float lo[8];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        if (b < batch) {
-            for (int c = tid; c < nchunk; c += 256) {
-                float f[8];
-                XLoad<T>::load(x + (int64_t)b * K + c * 8, f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] *= scale[b];
-                const int kb = c >> 3, qq = c & 7;  // chunk qq of the block: lane t = qq/2, half = qq%2
-                uint4* dst = sB + ((size_t)(kb * 2 + (qq & 1)) * ncols) * 4 + (qq >> 1);
-                dst[(b * PIECES) * 4] = pack_swapped(f);
-                if constexpr (PIECES == 2) {
-                    float lo[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        lo[i] = (f[i] - __half2float(__float2half_rn(f[i]))) * 2048.f;
-                    dst[(b * PIECES + 1) * 4] = pack_swapped(lo);
-                }
+                for (int i = 0; i < 8; ++i)
+                    lo[i] = (f[i] - __half2float(__float2half_rn(f[i]))) * 2048.f;
+                dst[4] = pack_swapped(lo);
             }
         }
     }
     __syncthreads();
+    if (n == 0) return;
 
-    // ---- 3. main loop: decode + MMA, U blocks in flight ----------------------------------------
+    // ---- 3. main loop over this warp's units -----------------------------------------------------
     float acc[NCOLT][4];
 #pragma unroll
     for (int c = 0; c < NCOLT; ++c)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
 
-    for (int kb0 = kb_begin; kb0 < kb_end; kb0 += kU) {
+    uint32_t tile = L0 / nkb, kb = L0 % nkb;
+    uint32_t seg_start_kb = kb;        // first block of the current tile segment
+    const uint32_t first_tile = tile;
+    const uint4* bsrc = sB + ((size_t)kb * 2 * ncols) * 4 + t;  // advances 2*ncols*4 per block
+    const uint32_t bstep = 2 * ncols * 4;
+
+    // finish one output element: scale, bias, convert, store
+    auto store_out = [&](float v, int b, uint32_t row) {
+        v *= sScale[b];
+        if (bias) v += DT<T>::to_f32(bias[row]);
+        out[(size_t)b * N + row] = DT<T>::from_f32(v);
+    };
+
+    // flush the accumulated partial sums of (tile, [seg_start_kb, kb_end)) -------------------------
+    auto flush = [&](uint32_t kb_end) {
+        const uint32_t seg_len = kb_end - seg_start_kb;
+        const uint32_t row0 = tile * 16;
+        if (seg_len == nkb) {
+            // this warp covered the whole tile: finish directly.
+            // acc[ct][i]: row g (+8 for i >= 2), column ct*8 + 2t + (i & 1)
+            if constexpr (PIECES == 1) {
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int kb = kb0 + u;
-            if (kb < kb_end) {
-                const uint2 w0 = q0[u], w1 = q1[u];
-                const float am0 = a0[u], am1 = a1[u];
-                const int kn = kb + kU;
-                if (kn < kb_end) {  // refill this slot
-                    q0[u] = ldg_stream_u2(p0 + kn * 32);
-                    q1[u] = ldg_stream_u2(p1 + kn * 32);
-                    a0[u] = load_absmax<NESTED>(absmax, nd, (e0 + (int64_t)kn * 64) >> bs_log2);
-                    a1[u] = load_absmax<NESTED>(absmax, nd, (e1 + (int64_t)kn * 64) >> bs_log2);
-                }
-                uint32_t ha[2][4], hb[2][4];  // [word][half2] for rows r0 / r1
-                decode_word(w0.x, ha[0]);
-                decode_word(w0.y, ha[1]);
-                decode_word(w1.x, hb[0]);
-                decode_word(w1.y, hb[1]);
+                for (int ct = 0; ct < NCOLT; ++ct)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int col = ct * 8 + 2 * t + (i & 1);
+                        if (col < batch) store_out(acc[ct][i], col, row0 + g + ((i & 2) ? 8 : 0));
+                    }
+            } else {
+                // columns (2b, 2b+1) = (hi, lo) of batch row b live in the same lane
 #pragma unroll
                 for (int ct = 0; ct < NCOLT; ++ct) {
-                    const int col = ct * 8 + g;
+                    const int b = ct * 4 + t;
+                    if (b < batch) {
+                        store_out(acc[ct][0] + acc[ct][1] * (1.f / 2048.f), b, row0 + g);
+                        store_out(acc[ct][2] + acc[ct][3] * (1.f / 2048.f), b, row0 + g + 8);
+                    }
+                }
+            }
+        } else {
+            // shared tile.  Contributors are the consecutive warps wa..wb whose ranges intersect it;
+            // each parks its partial in its slot (0 if the tile is where its range starts, else 1).
+            const uint32_t u_lo = tile * nkb, u_hi = u_lo + nkb;
+            const uint32_t wa = part.owner(u_lo), wb = part.owner(u_hi - 1);
+            const uint32_t slot = (tile == first_tile) ? 0u : 1u;
+            const bool local = (u_lo >= cta_L0) && (u_hi <= cta_L1);  // all contributors in this CTA
+            float* dst = local ? &sPart[warp][slot][0][0]
+                               : ws.partials + ((size_t)wid * 2 + slot) * 16 * NC;
+#pragma unroll
+            for (int ct = 0; ct < NCOLT; ++ct) {
+                float2* d2 = reinterpret_cast<float2*>(dst + ct * 8 + 2 * t);
+                d2[(g * NC) / 2] = make_float2(acc[ct][0], acc[ct][1]);
+                d2[((g + 8) * NC) / 2] = make_float2(acc[ct][2], acc[ct][3]);
+            }
+            if (local) __threadfence_block(); else __threadfence();
+            __syncwarp();
+            unsigned old = 0;
+            if (lane == 0)
+                old = local ? atomicAdd(&sCnt[wa - blockIdx.x * kWarps], seg_len)
+                            : atomicAdd(ws.counters + tile, seg_len);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old + seg_len == nkb) {
+                // last arriver: sum the contributors' slots in warp order (deterministic)
+                if (local) __threadfence_block(); else __threadfence();
+                for (int idx = lane; idx < 16 * batch; idx += 32) {
+                    const int row = idx & 15, b = idx >> 4;
+                    float v = 0.f;
+                    for (uint32_t wc = wa; wc <= wb; ++wc) {
+                        const uint32_t cslot = (part.begin(wc) / nkb == tile) ? 0u : 1u;
+                        float p0, p1 = 0.f;
+                        if (local) {
+                            const float* src = &sPart[wc - blockIdx.x * kWarps][cslot][row][b * PIECES];
+                            p0 = src[0];
+                            if constexpr (PIECES == 2) p1 = src[1];
+                        } else {
+                            const float* src = ws.partials + ((size_t)wc * 2 + cslot) * 16 * NC +
+                                               row * NC + b * PIECES;
+                            p0 = __ldcg(src);
+                            if constexpr (PIECES == 2) p1 = __ldcg(src + 1);
+                        }
+                        v += p0 + p1 * (1.f / 2048.f);
+                    }
+                    store_out(v, b, row0 + row);
+                }
+                if (lane == 0 && !local) ws.counters[tile] = 0;  // ready for the next launch
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCOLT; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+    };
+
+    for (uint32_t s0 = 0; s0 < n; s0 += kU) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t s = s0 + u;
+            if (s < n) {
+                uint32_t ha[2][4], hb[2][4];  // [word][half2] for rows g / g+8
+                decode_word(q0[u].x, ha[0]);
+                decode_word(q0[u].y, ha[1]);
+                decode_word(q1[u].x, hb[0]);
+                decode_word(q1[u].y, hb[1]);
+                const float am0 = a0[u], am1 = a1[u];
+                if (s + kU < n) issue_load(u);  // refill this slot
+#pragma unroll
+                for (int ct = 0; ct < NCOLT; ++ct) {
+                    const int col = ct * 8 + (int)g;
                     uint4 bA = make_uint4(0, 0, 0, 0), bB = make_uint4(0, 0, 0, 0);
                     if (col < ncols) {
-                        const uint4* src = sB + ((size_t)(kb * 2) * ncols + col) * 4 + t;
-                        bA = src[0];                       // k16 groups 0,1 (x elements 0..7 of the lane's 16)
-                        bB = src[(size_t)ncols * 4];       // k16 groups 2,3
+                        bA = bsrc[col * 4];                // k16 groups 0,1
+                        bB = bsrc[(ncols + col) * 4];      // k16 groups 2,3
                     }
                     float d[4] = {0.f, 0.f, 0.f, 0.f};
                     mma16816(d, ha[0][0], hb[0][0], ha[0][1], hb[0][1], bA.x, bA.y);
@@ -276,107 +377,89 @@ gemv_mma_kernel(const T* __restrict__ x, const uint8_t* __restrict__ packed,
                     acc[ct][2] = fmaf(am1, d[2], acc[ct][2]);
                     acc[ct][3] = fmaf(am1, d[3], acc[ct][3]);
                 }
+                ++kb;
+                bsrc += bstep;
+                if (kb == nkb || s + 1 == n) {
+                    flush(kb);
+                    if (kb == nkb) {
+                        kb = 0;
+                        ++tile;
+                        bsrc = sB + t;
+                    }
+                    seg_start_kb = kb;
+                }
             }
-        }
-    }
-
-    // ---- 4. combine the k-split warps and the pieces, add bias, store ----------------------------
-    constexpr int RC = 8 * NCOLT;
-#pragma unroll
-    for (int ct = 0; ct < NCOLT; ++ct) {
-        float* dst = sRed + (warp * 16) * RC + ct * 8 + 2 * t;
-        dst[g * RC] = acc[ct][0];
-        dst[g * RC + 1] = acc[ct][1];
-        dst[(g + 8) * RC] = acc[ct][2];
-        dst[(g + 8) * RC + 1] = acc[ct][3];
-    }
-    __syncthreads();
-    // one thread per (row tile, row, batch row)
-    for (int idx = tid; idx < RW * 16 * batch; idx += 256) {
-        const int b = idx % batch;
-        const int row = (idx / batch) & 15;
-        const int rtile = idx / (batch * 16);
-        const int grow = (blockIdx.x * RW + rtile) * 16 + row;
-        if (grow < N) {
-            float v = 0.f;
-            for (int kw = 0; kw < KW; ++kw) {
-                const float* src = sRed + (((rtile << kw_log2) + kw) * 16 + row) * RC + b * PIECES;
-                if constexpr (PIECES == 2) v += src[0] + src[1] * (1.f / 2048.f);
-                else v += src[0];
-            }
-            v *= sScale[b] * (1.f / 12.f);
-            if (bias) v += DT<T>::to_f32(bias[grow]);
-            out[(int64_t)b * N + grow] = DT<T>::from_f32(v);
         }
     }
 }
 
 struct Plan {
-    int kw_log2;
     int grid;
     size_t smem;
 };
 
-static size_t smem_bytes(int batch, int K, int pieces, int ncolt) {
+static size_t smem_bytes(int batch, int K, int pieces) {
     const size_t nkb = K / 64;
-    return nkb * 2 * (size_t)(batch * pieces) * 4 * 16 + (size_t)8 * 16 * 8 * ncolt * 4 + 64 * 4 +
-           8 * 4;
+    return nkb * 2 * (size_t)(batch * pieces) * 4 * 16;
 }
 
-static Plan make_plan(int batch, int N, int K, int pieces, int ncolt) {
-    static const int force_kw = [] {
-        const char* e = getenv("FP4_B200_GEMV_KW_LOG2");
-        return e ? atoi(e) : -1;
-    }();
-    const int ntiles = N / 16;
-    const int nkb = K / 64;
-    int kw_log2 = 0;
-    // prefer many rows per CTA (x staging is amortised over rows) while keeping >= ~2 CTAs per SM
-    // and at least kU blocks of work per warp
-    while (kw_log2 < 3) {
-        const int rw = 8 >> kw_log2;
-        const int ctas = (ntiles + rw - 1) / rw;
-        if (ctas >= 2 * kNumSMs) break;
-        if ((nkb >> (kw_log2 + 1)) < kU) break;
-        ++kw_log2;
-    }
-    if (force_kw >= 0 && force_kw <= 3) kw_log2 = force_kw;
-    const int rw = 8 >> kw_log2;
-    return Plan{kw_log2, (ntiles + rw - 1) / rw, smem_bytes(batch, K, pieces, ncolt)};
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 template <typename T, int NCOLT, bool NESTED>
 static int launch(const void* x, const uint8_t* packed, const float* absmax, const NestedDev& nd,
-                  const void* bias, void* out, int batch, int N, int K, int bs_log2,
-                  cudaStream_t st) {
+                  const void* bias, void* out, void* workspace, size_t workspace_bytes, int batch,
+                  int N, int K, int bs_log2, cudaStream_t st) {
     constexpr int PIECES = (sizeof(T) == 4) ? 2 : 1;
-    const Plan p = make_plan(batch, N, K, PIECES, NCOLT);
+    constexpr int NC = 8 * NCOLT;
     auto kern = gemv_mma_kernel<T, NCOLT, NESTED>;
-    if (p.smem > 48 * 1024) {
-        static size_t configured = 0;  // per template instantiation
-        if (p.smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 200 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            configured = 200 * 1024;
-        }
+    const size_t smem = smem_bytes(batch, K, PIECES);
+    static bool configured = false;  // per template instantiation
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
     }
-    kern<<<p.grid, 256, p.smem, st>>>((const T*)x, packed, absmax, nd, (const T*)bias, (T*)out,
-                                      batch, N, K, bs_log2, p.kw_log2);
+    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", 0);
+    static const int min_units = env_int("FP4_B200_GEMV_MIN_UNITS", 8);
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return FP4_B200_ERR_UNSUPPORTED;
+    if (occ > 4) occ = 4;  // the workspace is sized for <= 4 CTAs per SM
+    if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
+    const int64_t units = (int64_t)(N / 16) * (K / 64);
+    int64_t grid = (int64_t)kNumSMs * occ;
+    const int64_t max_by_work = (units + (int64_t)kWarps * min_units - 1) / ((int64_t)kWarps * min_units);
+    if (grid > max_by_work) grid = max_by_work;
+    if (grid < 1) grid = 1;
+    // workspace: counters [ntiles] + partials [W][2][16][NC]
+    const size_t need = kCounterBytes + (size_t)grid * kWarps * 2 * 16 * NC * 4;
+    if (!workspace || workspace_bytes < need) return FP4_B200_ERR_WORKSPACE;
+    Workspace ws;
+    ws.counters = reinterpret_cast<unsigned*>(workspace);
+    ws.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
+                                           kCounterBytes);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>((const T*)x, packed, absmax, nd, (const T*)bias,
+                                                 (T*)out, ws, batch, N, K, bs_log2 - 6);
     return (int)cudaGetLastError();
 }
 
 template <typename T>
 static int launch_t(const void* x, const uint8_t* packed, const float* absmax, bool nested,
-                    const NestedDev& nd, const void* bias, void* out, int batch, int N, int K,
-                    int bs_log2, cudaStream_t st) {
+                    const NestedDev& nd, const void* bias, void* out, void* workspace,
+                    size_t workspace_bytes, int batch, int N, int K, int bs_log2, cudaStream_t st) {
     constexpr int PIECES = (sizeof(T) == 4) ? 2 : 1;
     const bool two = batch * PIECES > 8;
-    if (nested)
-        return two ? launch<T, 2, true>(x, packed, absmax, nd, bias, out, batch, N, K, bs_log2, st)
-                   : launch<T, 1, true>(x, packed, absmax, nd, bias, out, batch, N, K, bs_log2, st);
-    return two ? launch<T, 2, false>(x, packed, absmax, nd, bias, out, batch, N, K, bs_log2, st)
-               : launch<T, 1, false>(x, packed, absmax, nd, bias, out, batch, N, K, bs_log2, st);
+#define FP4_GO(NCT, NST)                                                                         \
+    launch<T, NCT, NST>(x, packed, absmax, nd, bias, out, workspace, workspace_bytes, batch, N, K, \
+                        bs_log2, st)
+    if (nested) return two ? FP4_GO(2, true) : FP4_GO(1, true);
+    return two ? FP4_GO(2, false) : FP4_GO(1, false);
+#undef FP4_GO
 }
 
 }  // namespace
@@ -384,24 +467,32 @@ static int launch_t(const void* x, const uint8_t* packed, const float* absmax, b
 bool gemv_imma_supported(int batch, int N, int K, int blocksize, int dtype) {
     if (batch < 1 || batch > 8 || N <= 0 || K <= 0) return false;
     if (K % 64 != 0 || blocksize % 64 != 0 || N % 16 != 0) return false;
+    if ((int64_t)N * K / 64 >= (int64_t)1 << 31) return false;  // 32-bit unit cursors
+    if ((size_t)(N / 16) * 4 > kCounterBytes) return false;
     const int pieces = dtype == FP4_B200_F32 ? 2 : 1;
-    const int ncolt = batch * pieces > 8 ? 2 : 1;
-    return smem_bytes(batch, K, pieces, ncolt) <= 200 * 1024;
+    return smem_bytes(batch, K, pieces) <= 200 * 1024;
+}
+
+size_t gemv_imma_workspace_bytes(int /*N*/) {
+    // counters + the largest partial area any launch can need: 3 CTAs/SM x 8 warps x 2 slots x 16 x 16 floats
+    return kCounterBytes + (size_t)kNumSMs * 4 * kWarps * 2 * 16 * 16 * 4;
 }
 
 int gemv_imma_dispatch(const void* x, const uint8_t* packed, const float* absmax,
                        const fp4_b200_nested_t* nested, const NestedDev& nd, const void* bias,
-                       void* out, int batch, int N, int K, int bs_log2, int dtype,
-                       cudaStream_t st) {
+                       void* out, void* workspace, size_t workspace_bytes, int batch, int N, int K,
+                       int bs_log2, int dtype, cudaStream_t st) {
     const bool nst = nested != nullptr;
     switch (dtype) {
         case FP4_B200_F16:
-            return launch_t<__half>(x, packed, absmax, nst, nd, bias, out, batch, N, K, bs_log2, st);
+            return launch_t<__half>(x, packed, absmax, nst, nd, bias, out, workspace,
+                                    workspace_bytes, batch, N, K, bs_log2, st);
         case FP4_B200_BF16:
-            return launch_t<__nv_bfloat16>(x, packed, absmax, nst, nd, bias, out, batch, N, K,
-                                           bs_log2, st);
+            return launch_t<__nv_bfloat16>(x, packed, absmax, nst, nd, bias, out, workspace,
+                                           workspace_bytes, batch, N, K, bs_log2, st);
         case FP4_B200_F32:
-            return launch_t<float>(x, packed, absmax, nst, nd, bias, out, batch, N, K, bs_log2, st);
+            return launch_t<float>(x, packed, absmax, nst, nd, bias, out, workspace,
+                                   workspace_bytes, batch, N, K, bs_log2, st);
         default:
             return FP4_B200_ERR_DTYPE;
     }

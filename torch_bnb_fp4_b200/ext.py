@@ -115,6 +115,26 @@ def code_is_bnb_fp4(code: torch.Tensor) -> bool:
     return ok
 
 
+# ---- GEMV workspace --------------------------------------------------------------------------------
+# The stream-K GEMV parks partial sums of row tiles shared between warps in a small scratch buffer
+# (include/fp4_b200.h).  One zero-filled buffer per (device, stream), grown on demand; launches on the
+# same stream are ordered, so sharing it between layers is safe.
+_workspaces: dict = {}
+
+
+def _gemv_workspace(device: torch.device, stream_ptr: int, n_out: int):
+    need = lib.fp4_b200_gemv_workspace_bytes(n_out)
+    key = (device.index, stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("GEMV workspace must be created before CUDA-graph capture: run the "
+                               "layer once eagerly (warm-up) on the capturing stream first")
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 def make_nested(qabsmax: torch.Tensor, code2: torch.Tensor, absmax2: torch.Tensor, offset: float,
                 blocksize2: int) -> Nested:
     """Pack a bitsandbytes nested state (state2 + offset) for the *_nested entry points."""
@@ -198,8 +218,8 @@ def _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags,
     if A.dtype != dt:
         raise RuntimeError(f"A is {A.dtype} but dtype argument says {dt}")
     n_out, k = int(Bshape[0]), int(Bshape[1])
-    if A.dim() not in (2, 3) or A.shape[-1] != k:
-        raise RuntimeError(f"A must be [batch, {k}] or [b0, b1, {k}], got {tuple(A.shape)}")
+    if A.dim() < 1 or A.shape[-1] != k:
+        raise RuntimeError(f"A must be [..., {k}], got {tuple(A.shape)}")
     batch = A.numel() // k if k else 0
     if B.numel() * 2 < n_out * k:
         raise RuntimeError("B holds fewer than N*K/2 bytes")
@@ -213,12 +233,13 @@ def _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags,
     if datatype is not None and code_is_bnb_fp4(datatype):
         flags |= _lib.FLAG_CODE_IS_BNB_FP4
     with _on_device(A) as st:
+        ws = _gemv_workspace(A.device, st, n_out)
         check(lib.fp4_b200_gemv(
             A.data_ptr(), B.data_ptr(), None if absmax is None else absmax.data_ptr(),
             None if nested is None else ctypes.byref(nested),
             None if datatype is None else datatype.data_ptr(),
             None if bias is None else bias.data_ptr(), out.data_ptr(), batch, n_out, k, blocksize,
-            _CODE_OF[dt], flags, st), what)
+            _CODE_OF[dt], flags, ws.data_ptr(), ws.numel(), st), what)
     return out
 
 
