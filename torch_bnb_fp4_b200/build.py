@@ -22,6 +22,7 @@ def _deps_mtime() -> float:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
+    extra = os.environ.get("FP4_B200_NVCC_EXTRA", "").split()  # experiments, e.g. -DFP4_GEMV_MIN_CTAS=3
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdr_m = _deps_mtime()
@@ -32,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:

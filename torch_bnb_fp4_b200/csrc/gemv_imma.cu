@@ -38,12 +38,15 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace fp4b200 {
 
 namespace {
 
-constexpr int kU = 4;        // units in flight per lane (per row)
+#ifndef FP4_GEMV_MIN_CTAS
+#define FP4_GEMV_MIN_CTAS 2
+#endif
 constexpr int kWarps = 8;    // warps per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr size_t kCounterBytes = 256 * 1024;  // fixed-size counter region: 65536 row tiles (N <= 2^20)
@@ -61,11 +64,13 @@ __device__ __forceinline__ void unpack_e5m2x4(uint32_t m, uint32_t& h01, uint32_
 
 // 8 nibbles (one 32-bit word of packed weights) -> 4 x half2 of 12*code[nibble].
 // h[j] holds nibbles (2j, 2j+1) of the word = elements (2*byte+1, 2*byte) of packed byte j.
-__device__ __forceinline__ void decode_word(uint32_t w, uint32_t (&h)[4]) {
+__device__ __forceinline__ void decode_word(uint32_t w, uint32_t tab_lo, uint32_t (&h)[4]) {
     const uint32_t wm = w & 0x77777777u;           // magnitude index of every nibble
-    const uint32_t w4 = w << 4;                    // brings even nibbles' sign bits to byte msbs
-    const uint32_t mag_lo = prmt(kTabLo, kTabHi, wm);        // nibbles 0..3 -> bytes 0..3
-    const uint32_t mag_hi = prmt(kTabLo, kTabHi, wm >> 16);  // nibbles 4..7
+    // the two shifts are done as integer multiplies so they issue on the FMA pipe; the ALU pipe
+    // (PRMT / LOP3 / F2FP, half rate) is the one this kernel saturates
+    const uint32_t w4 = w * 16u;                   // brings even nibbles' sign bits to byte msbs
+    const uint32_t mag_lo = prmt(tab_lo, kTabHi, wm);                    // nibbles 0..3 -> bytes 0..3
+    const uint32_t mag_hi = prmt(tab_lo, kTabHi, __umulhi(wm, 65536u));  // nibbles 4..7 (wm >> 16)
     // sign-replicate mode (selector msb): byte = 0xFF if the selected source byte is negative
     const uint32_t sg_lo = prmt(w, w4, 0x9D8Cu);  // signs of nibbles 0,1,2,3
     const uint32_t sg_hi = prmt(w, w4, 0xBFAEu);  // signs of nibbles 4,5,6,7
@@ -132,13 +137,35 @@ __device__ __forceinline__ uint4 pack_swapped(const float (&v)[8]) {
     return r;
 }
 
+// Division by a launch-time constant without the ~40-instruction udiv sequence (Granlund-Montgomery
+// round-up method; exact for n < 2^31, which gemv_imma_supported guarantees for unit indices).
+struct FastDiv {
+    uint32_t d, mul, shift;
+    FastDiv() = default;
+    explicit FastDiv(uint32_t div) : d(div) {
+        if (div <= 1) { mul = 0; shift = 0; return; }
+        uint32_t l = 0;
+        while ((1ull << l) < div) ++l;   // ceil(log2 d)
+        shift = l - 1;
+        mul = (uint32_t)(((1ull << (32 + shift)) + div - 1) / div);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const {
+        return d <= 1 ? n : (__umulhi(n, mul) >> shift);
+    }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+
 // Balanced flat partition of B units over W warps: the first r = B % W warps get q+1 units.
 struct Partition {
     uint32_t q, r;
+    FastDiv by_q, by_q1;
     __device__ __forceinline__ uint32_t begin(uint32_t w) const { return w * q + (w < r ? w : r); }
     __device__ __forceinline__ uint32_t owner(uint32_t u) const {  // warp whose range holds unit u
         const uint32_t big = r * (q + 1);
-        return u < big ? u / (q + 1) : r + (u - big) / q;
+        return u < big ? by_q1.div(u) : r + by_q.div(u - big);
     }
 };
 
@@ -147,19 +174,138 @@ struct Workspace {
     float* partials;     // [W][2][16][NC] fp32
 };
 
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(saddr));
+    return r;
+}
+
+// Everything the (rare, out-of-line) tile combine needs.
+template <typename T, int NC>
+struct FlushCtx {
+    const float* sScale;
+    float* sPart;        // [kWarps][2][16][NC]
+    unsigned* sCnt;      // [kWarps]
+    const T* bias;
+    T* out;
+    Workspace ws;
+    Partition part;
+    FastDiv by_nkb;
+    uint32_t nkb, wid, first_tile, cta_L0, cta_L1, cta_w0;
+    int batch, N;
+};
+
+// Combine / store the partial sums `acc` of (tile, k blocks [seg_start_kb, kb_end)).  Called once per
+// row tile and warp, so it is kept out of the streaming loop (noinline).
+template <int NCOLT>
+struct AccV {
+    float v[NCOLT][4];
+};
+
+template <typename T, int NCOLT>
+__device__ __noinline__ void flush_tile(const FlushCtx<T, 8 * NCOLT>& c, const AccV<NCOLT> accv,
+                                        uint32_t tile, uint32_t seg_start_kb, uint32_t kb_end) {
+    constexpr int PIECES = (sizeof(T) == 4) ? 2 : 1;
+    constexpr int NC = 8 * NCOLT;
+    const float (&acc)[NCOLT][4] = accv.v;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = lane >> 2, t = lane & 3;
+    const uint32_t seg_len = kb_end - seg_start_kb;
+    const uint32_t row0 = tile * 16;
+    auto store_out = [&](float v, int b, uint32_t row) {
+        v *= c.sScale[b];
+        if (c.bias) v += DT<T>::to_f32(c.bias[row]);
+        c.out[(size_t)b * c.N + row] = DT<T>::from_f32(v);
+    };
+    if (seg_len == c.nkb) {
+        // this warp covered the whole tile: finish directly.
+        // acc[ct][i]: row g (+8 for i >= 2), column ct*8 + 2t + (i & 1)
+        if constexpr (PIECES == 1) {
+#pragma unroll
+            for (int ct = 0; ct < NCOLT; ++ct)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int col = ct * 8 + 2 * t + (i & 1);
+                    if (col < c.batch) store_out(acc[ct][i], col, row0 + g + ((i & 2) ? 8 : 0));
+                }
+        } else {
+            // columns (2b, 2b+1) = (hi, lo) of batch row b live in the same lane
+#pragma unroll
+            for (int ct = 0; ct < NCOLT; ++ct) {
+                const int b = ct * 4 + t;
+                if (b < c.batch) {
+                    store_out(acc[ct][0] + acc[ct][1] * (1.f / 2048.f), b, row0 + g);
+                    store_out(acc[ct][2] + acc[ct][3] * (1.f / 2048.f), b, row0 + g + 8);
+                }
+            }
+        }
+        return;
+    }
+    // shared tile.  Contributors are the consecutive warps wa..wb whose ranges intersect it; each
+    // parks its partial in its slot (0 if the tile is where its range starts, else 1).
+    const uint32_t u_lo = tile * c.nkb, u_hi = u_lo + c.nkb;
+    const uint32_t wa = c.part.owner(u_lo), wb = c.part.owner(u_hi - 1);
+    const uint32_t slot = (tile == c.first_tile) ? 0u : 1u;
+    const bool local = (u_lo >= c.cta_L0) && (u_hi <= c.cta_L1);  // all contributors in this CTA
+    float* dst = local ? c.sPart + ((size_t)warp * 2 + slot) * 16 * NC
+                       : c.ws.partials + ((size_t)c.wid * 2 + slot) * 16 * NC;
+#pragma unroll
+    for (int ct = 0; ct < NCOLT; ++ct) {
+        float2* d2 = reinterpret_cast<float2*>(dst + ct * 8 + 2 * t);
+        d2[(g * NC) / 2] = make_float2(acc[ct][0], acc[ct][1]);
+        d2[((g + 8) * NC) / 2] = make_float2(acc[ct][2], acc[ct][3]);
+    }
+    if (local) __threadfence_block(); else __threadfence();
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0)
+        old = local ? atomicAdd(c.sCnt + (wa - c.cta_w0), seg_len)
+                    : atomicAdd(c.ws.counters + tile, seg_len);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old + seg_len != c.nkb) return;
+    // last arriver: sum the contributors' slots in warp order (deterministic)
+    if (local) __threadfence_block(); else __threadfence();
+    // contributor wa starts at or before the tile (slot 0 only if it starts inside it); every later
+    // contributor starts inside the tile (slot 0)
+    const uint32_t slot_a = (c.part.begin(wa) >= u_lo) ? 0u : 1u;
+    for (int idx = lane; idx < 16 * c.batch; idx += 32) {
+        const int row = idx & 15, b = idx >> 4;
+        float v = 0.f;
+        for (uint32_t wc = wa; wc <= wb; ++wc) {
+            const uint32_t cslot = (wc == wa) ? slot_a : 0u;
+            float p0, p1 = 0.f;
+            if (local) {
+                const float* src = c.sPart + (((size_t)(wc - c.cta_w0) * 2 + cslot) * 16 + row) * NC + b * PIECES;
+                p0 = src[0];
+                if constexpr (PIECES == 2) p1 = src[1];
+            } else {
+                const float* src = c.ws.partials + (((size_t)wc * 2 + cslot) * 16 + row) * NC + b * PIECES;
+                p0 = __ldcg(src);
+                if constexpr (PIECES == 2) p1 = __ldcg(src + 1);
+            }
+            v += p0 + p1 * (1.f / 2048.f);
+        }
+        store_out(v, b, row0 + row);
+    }
+    if (lane == 0 && !local) c.ws.counters[tile] = 0;  // ready for the next launch
+}
+
 // T: activation dtype.  PIECES = 1 (fp16/bf16 x: one fp16 column per batch row) or 2 (fp32 x: hi + lo).
 // NCOLT = number of 8-column MMA tiles (1, or 2 when batch*PIECES > 8).
 template <typename T, int NCOLT, bool NESTED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FP4_GEMV_MIN_CTAS)
 gemv_mma_kernel(const T* __restrict__ x, const uint8_t* __restrict__ packed,
                 const float* __restrict__ absmax, const NestedDev nd, const T* __restrict__ bias,
                 T* __restrict__ out, const Workspace ws, const int batch, const int N, const int K,
-                const int am_shift /* log2(blocksize / 64) */) {
+                const int am_shift /* log2(blocksize / 64) */, const Partition part,
+                const FastDiv by_nkb) {
     constexpr int PIECES = (sizeof(T) == 4) ? 2 : 1;
     constexpr int NC = 8 * NCOLT;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ float sPart[kWarps][2][16][NC];  // CTA-local partial sums of shared row tiles
-    __shared__ unsigned sCnt[kWarps];           // units accounted for, by first contributing warp
+    __shared__ float sPart[kWarps * 2 * 16 * NC];  // CTA-local partial sums of shared row tiles
+    __shared__ unsigned sCnt[kWarps];              // units accounted for, by first contributing warp
     __shared__ float sMax[kWarps * 8];
     __shared__ float sScale[8];
     const uint32_t nkb = (uint32_t)K >> 6;
@@ -169,41 +315,75 @@ gemv_mma_kernel(const T* __restrict__ x, const uint8_t* __restrict__ packed,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t g = lane >> 2, t = lane & 3;
 
-    const uint32_t ntiles = (uint32_t)N >> 4;
-    const uint32_t B = ntiles * nkb;
     const uint32_t W = gridDim.x * kWarps;
-    const Partition part{B / W, B % W};
     const uint32_t wid = blockIdx.x * kWarps + warp;
-    const uint32_t L0 = part.begin(wid), L1 = part.begin(wid + 1);
-    const uint32_t n = L1 - L0;
-    const uint32_t cta_L0 = part.begin(blockIdx.x * kWarps), cta_L1 = part.begin((blockIdx.x + 1) * kWarps);
+    const uint32_t L0 = part.begin(wid);
+    const uint32_t n = part.begin(wid + 1) - L0;
     if (tid < kWarps) sCnt[tid] = 0;
+#ifdef FP4_GEMV_TIMELINE
+    long long tl[5];
+    tl[0] = clock64();
+#endif
 
-    // ---- load cursor: unit L -> (tile, kb); offsets advance by constant steps with a wrap -------
-    // index in 64-element units of (row tile*16+g, kb): (tile*16+g)*nkb + kb; the packed bytes sit at
-    // 32 x that (+ 8t), the absmax at that >> am_shift
-    uint32_t ld_kb = n ? L0 % nkb : 0;
-    uint32_t ld_u64 = n ? ((L0 / nkb) * 16 + g) * nkb + ld_kb : 0;
-    const uint32_t wrap_u64 = 15 * nkb + 1;  // from the last block of a tile to block 0 of the next
-    const uint8_t* wp = packed + 8 * t;
-    const uint32_t r8 = 8 * nkb;             // +8 rows, in 64-element units
+    // ---- weight-stream cursor ---------------------------------------------------------------------
+    // unit L -> (tile, kb).  Row g of the tile at block kb starts at packed + ((tile*16+g)*nkb + kb)*32;
+    // this lane reads 8 bytes at + 8t, and the same for row g+8 (+ row8 bytes).
+    uint32_t ld_left = n;                       // units not yet requested
+    uint32_t tile0, ld_kb;
+    by_nkb.divmod(n ? L0 : 0, tile0, ld_kb);    // first unit -> (row tile, k block)
+    const uint32_t ld_kb_first = ld_kb;
+    const uint8_t* ld_ptr = packed + ((size_t)((tile0 * 16 + g) * nkb + ld_kb)) * 32 + 8 * t;
+    const uint32_t row8 = 8 * nkb * 32;         // bytes from row g to row g+8
+    const uint32_t tile_skip = 15 * nkb * 32;   // extra bytes when stepping into the next row tile
 
-    uint2 q0[kU], q1[kU];
-    float a0[kU], a1[kU];
-    auto issue_load = [&](int u) {
-        q0[u] = ldg_stream_u2(wp + (size_t)ld_u64 * 32);
-        q1[u] = ldg_stream_u2(wp + (size_t)(ld_u64 + r8) * 32);
-        a0[u] = load_absmax<NESTED>(absmax, nd, (int64_t)(ld_u64 >> am_shift));
-        a1[u] = load_absmax<NESTED>(absmax, nd, (int64_t)((ld_u64 + r8) >> am_shift));
-        const bool wrap = (++ld_kb == nkb);
-        ld_u64 += wrap ? wrap_u64 : 1u;
-        if (wrap) ld_kb = 0;
+    uint2 qa0[4], qa1[4], qb0[4], qb1[4];       // two groups of 4 units in flight, rows g / g+8
+    auto load_unit = [&](uint2& d0, uint2& d1) {  // generic: one unit, with tile wrap
+        if (ld_left) {
+            d0 = ldg_stream_u2(ld_ptr);
+            d1 = ldg_stream_u2(ld_ptr + row8);
+            --ld_left;
+            ld_ptr += 32;
+            if (++ld_kb == nkb) {
+                ld_kb = 0;
+                ld_ptr += tile_skip;
+            }
+        }
     };
-    // ---- 1. put the first kU units of the weight stream in flight ------------------------------
+    // absmax: the four lanes of a quad would all fetch the same value; instead lane t fetches the value
+    // of unit (group base + t) - one load per lane per 4 units, 4x fewer L1 wavefronts - and the quad
+    // exchanges them with shuffles.
+    uint32_t am_kb = ld_kb + t, am_u64 = (tile0 * 16 + g) * nkb + ld_kb + t;
+    while (am_kb >= nkb) {
+        am_kb -= nkb;
+        am_u64 += 15 * nkb;
+    }
+    const uint32_t r8u = 8 * nkb;
+    uint32_t am_unit = t;  // index (within the warp's range) of the unit this lane fetches next
+    float amA0 = 0.f, amA1 = 0.f, amB0 = 0.f, amB1 = 0.f;  // next group / the one after, rows g / g+8
+    auto issue_absmax = [&](float& d0, float& d1) {
+        if (am_unit < n) {
+            d0 = load_absmax<NESTED>(absmax, nd, (int64_t)(am_u64 >> am_shift));
+            d1 = load_absmax<NESTED>(absmax, nd, (int64_t)((am_u64 + r8u) >> am_shift));
+        }
+        am_unit += 4;
+        am_kb += 4;
+        am_u64 += 4;
+        while (am_kb >= nkb) {  // crossed into the next row tile(s)
+            am_kb -= nkb;
+            am_u64 += 15 * nkb;
+        }
+    };
+    // ---- 1. put the first 8 units of the weight stream in flight --------------------------------
 #pragma unroll
-    for (int u = 0; u < kU; ++u)
-        if ((uint32_t)u < n) issue_load(u);
+    for (int u = 0; u < 4; ++u) load_unit(qa0[u], qa1[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_unit(qb0[u], qb1[u]);
+    issue_absmax(amA0, amA1);
+    issue_absmax(amB0, amB1);
 
+#ifdef FP4_GEMV_TIMELINE
+    tl[1] = clock64();
+#endif
     // ---- 2. stage x as scaled fp16 in B-fragment order (once per CTA) --------------------------
     const int nchunk = K >> 3;  // 8-element chunks per batch row
     for (int b = 0; b < batch; ++b) {  // pass 1: max |x| per batch row
@@ -245,152 +425,138 @@ gemv_mma_kernel(const T* __restrict__ x, const uint8_t* __restrict__ packed,
         }
     }
     __syncthreads();
+#ifdef FP4_GEMV_TIMELINE
+    tl[2] = clock64();
+#endif
     if (n == 0) return;
 
     // ---- 3. main loop over this warp's units -----------------------------------------------------
-    float acc[NCOLT][4];
+    FlushCtx<T, NC> fc;
+    fc.sScale = sScale; fc.sPart = sPart; fc.sCnt = sCnt; fc.bias = bias; fc.out = out; fc.ws = ws;
+    fc.part = part; fc.nkb = nkb; fc.wid = wid; fc.first_tile = tile0; fc.by_nkb = by_nkb;
+    fc.cta_w0 = blockIdx.x * kWarps;
+    fc.cta_L0 = part.begin(fc.cta_w0); fc.cta_L1 = part.begin(fc.cta_w0 + kWarps);
+    fc.batch = batch; fc.N = N;
+
+    AccV<NCOLT> acc;
 #pragma unroll
     for (int c = 0; c < NCOLT; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc.v[c][i] = 0.f;
 
-    uint32_t tile = L0 / nkb, kb = L0 % nkb;
-    uint32_t seg_start_kb = kb;        // first block of the current tile segment
-    const uint32_t first_tile = tile;
-    const uint4* bsrc = sB + ((size_t)kb * 2 * ncols) * 4 + t;  // advances 2*ncols*4 per block
-    const uint32_t bstep = 2 * ncols * 4;
+    uint32_t tile = tile0, kb = ld_kb_first;
+    uint32_t seg_start_kb = kb;  // first block of the current tile segment
+    // shared-space byte address of this lane's B fragments for block kb and column tile 0:
+    //   sB[(kb*2 + h)*ncols*4 + col*4 + t];  lanes whose column does not exist read column 0 instead
+    //   (their accumulator columns are never stored), so the loads need no predicate
+    const uint32_t bstep = 2 * ncols * 4 * 16;   // bytes per k block
+    const uint32_t bhalf = ncols * 4 * 16;       // bytes between the two halves of a block
+    uint32_t bcol[NCOLT];
+#pragma unroll
+    for (int ct = 0; ct < NCOLT; ++ct) {
+        const int col = ct * 8 + (int)g;
+        bcol[ct] = (col < ncols ? col : 0) * 64;
+    }
+    const uint32_t sB_base = (uint32_t)__cvta_generic_to_shared(sB) + t * 16;
+    uint32_t bsaddr = sB_base + kb * bstep;
+    uint32_t tab_lo;
+    asm volatile("mov.b32 %0, 0x4A482C00;" : "=r"(tab_lo));  // kTabLo, pinned in a register
+    const uint32_t quad = lane & ~3u;
 
-    // finish one output element: scale, bias, convert, store
-    auto store_out = [&](float v, int b, uint32_t row) {
-        v *= sScale[b];
-        if (bias) v += DT<T>::to_f32(bias[row]);
-        out[(size_t)b * N + row] = DT<T>::from_f32(v);
-    };
-
-    // flush the accumulated partial sums of (tile, [seg_start_kb, kb_end)) -------------------------
-    auto flush = [&](uint32_t kb_end) {
-        const uint32_t seg_len = kb_end - seg_start_kb;
-        const uint32_t row0 = tile * 16;
-        if (seg_len == nkb) {
-            // this warp covered the whole tile: finish directly.
-            // acc[ct][i]: row g (+8 for i >= 2), column ct*8 + 2t + (i & 1)
-            if constexpr (PIECES == 1) {
+    // FULL: the group holds 4 units and its slots are refilled (steady state, no per-unit checks);
+    // otherwise `cnt` (< 4 possible) units are consumed and nothing is refilled (tail).
+    auto consume_group = [&](uint2 (&q0)[4], uint2 (&q1)[4], auto full_tag, const uint32_t cnt) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const float gA0 = amA0, gA1 = amA1;  // this group's absmax, one unit per lane of the quad
+        amA0 = amB0;
+        amA1 = amB1;
+        issue_absmax(amB0, amB1);            // two groups ahead
+        // fast refill: the group 8 units ahead lies inside one row tile -> immediate offsets
+        const bool fast = FULL && ld_left >= 4 && ld_kb + 4 <= nkb;
+        const uint8_t* rp0 = ld_ptr;
+        const uint8_t* rp1 = ld_ptr + row8;
 #pragma unroll
-                for (int ct = 0; ct < NCOLT; ++ct)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int col = ct * 8 + 2 * t + (i & 1);
-                        if (col < batch) store_out(acc[ct][i], col, row0 + g + ((i & 2) ? 8 : 0));
-                    }
-            } else {
-                // columns (2b, 2b+1) = (hi, lo) of batch row b live in the same lane
-#pragma unroll
-                for (int ct = 0; ct < NCOLT; ++ct) {
-                    const int b = ct * 4 + t;
-                    if (b < batch) {
-                        store_out(acc[ct][0] + acc[ct][1] * (1.f / 2048.f), b, row0 + g);
-                        store_out(acc[ct][2] + acc[ct][3] * (1.f / 2048.f), b, row0 + g + 8);
-                    }
-                }
-            }
-        } else {
-            // shared tile.  Contributors are the consecutive warps wa..wb whose ranges intersect it;
-            // each parks its partial in its slot (0 if the tile is where its range starts, else 1).
-            const uint32_t u_lo = tile * nkb, u_hi = u_lo + nkb;
-            const uint32_t wa = part.owner(u_lo), wb = part.owner(u_hi - 1);
-            const uint32_t slot = (tile == first_tile) ? 0u : 1u;
-            const bool local = (u_lo >= cta_L0) && (u_hi <= cta_L1);  // all contributors in this CTA
-            float* dst = local ? &sPart[warp][slot][0][0]
-                               : ws.partials + ((size_t)wid * 2 + slot) * 16 * NC;
-#pragma unroll
-            for (int ct = 0; ct < NCOLT; ++ct) {
-                float2* d2 = reinterpret_cast<float2*>(dst + ct * 8 + 2 * t);
-                d2[(g * NC) / 2] = make_float2(acc[ct][0], acc[ct][1]);
-                d2[((g + 8) * NC) / 2] = make_float2(acc[ct][2], acc[ct][3]);
-            }
-            if (local) __threadfence_block(); else __threadfence();
-            __syncwarp();
-            unsigned old = 0;
-            if (lane == 0)
-                old = local ? atomicAdd(&sCnt[wa - blockIdx.x * kWarps], seg_len)
-                            : atomicAdd(ws.counters + tile, seg_len);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old + seg_len == nkb) {
-                // last arriver: sum the contributors' slots in warp order (deterministic)
-                if (local) __threadfence_block(); else __threadfence();
-                for (int idx = lane; idx < 16 * batch; idx += 32) {
-                    const int row = idx & 15, b = idx >> 4;
-                    float v = 0.f;
-                    for (uint32_t wc = wa; wc <= wb; ++wc) {
-                        const uint32_t cslot = (part.begin(wc) / nkb == tile) ? 0u : 1u;
-                        float p0, p1 = 0.f;
-                        if (local) {
-                            const float* src = &sPart[wc - blockIdx.x * kWarps][cslot][row][b * PIECES];
-                            p0 = src[0];
-                            if constexpr (PIECES == 2) p1 = src[1];
-                        } else {
-                            const float* src = ws.partials + ((size_t)wc * 2 + cslot) * 16 * NC +
-                                               row * NC + b * PIECES;
-                            p0 = __ldcg(src);
-                            if constexpr (PIECES == 2) p1 = __ldcg(src + 1);
-                        }
-                        v += p0 + p1 * (1.f / 2048.f);
-                    }
-                    store_out(v, b, row0 + row);
-                }
-                if (lane == 0 && !local) ws.counters[tile] = 0;  // ready for the next launch
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NCOLT; ++c)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
-    };
-
-    for (uint32_t s0 = 0; s0 < n; s0 += kU) {
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const uint32_t s = s0 + u;
-            if (s < n) {
+        for (int u = 0; u < 4; ++u) {
+            if (FULL || (uint32_t)u < cnt) {
                 uint32_t ha[2][4], hb[2][4];  // [word][half2] for rows g / g+8
-                decode_word(q0[u].x, ha[0]);
-                decode_word(q0[u].y, ha[1]);
-                decode_word(q1[u].x, hb[0]);
-                decode_word(q1[u].y, hb[1]);
-                const float am0 = a0[u], am1 = a1[u];
-                if (s + kU < n) issue_load(u);  // refill this slot
+                decode_word(q0[u].x, tab_lo, ha[0]);
+                decode_word(q0[u].y, tab_lo, ha[1]);
+                decode_word(q1[u].x, tab_lo, hb[0]);
+                decode_word(q1[u].y, tab_lo, hb[1]);
+                if (fast) {  // the slot's registers are dead now: refill them
+                    q0[u] = ldg_stream_u2(rp0 + 32 * u);
+                    q1[u] = ldg_stream_u2(rp1 + 32 * u);
+                }
+                const float am0 = __shfl_sync(0xffffffffu, gA0, quad | u);
+                const float am1 = __shfl_sync(0xffffffffu, gA1, quad | u);
 #pragma unroll
                 for (int ct = 0; ct < NCOLT; ++ct) {
-                    const int col = ct * 8 + (int)g;
-                    uint4 bA = make_uint4(0, 0, 0, 0), bB = make_uint4(0, 0, 0, 0);
-                    if (col < ncols) {
-                        bA = bsrc[col * 4];                // k16 groups 0,1
-                        bB = bsrc[(ncols + col) * 4];      // k16 groups 2,3
-                    }
+                    const uint4 bA = lds_u4(bsaddr + bcol[ct]);          // k16 groups 0,1
+                    const uint4 bB = lds_u4(bsaddr + bhalf + bcol[ct]);  // k16 groups 2,3
                     float d[4] = {0.f, 0.f, 0.f, 0.f};
                     mma16816(d, ha[0][0], hb[0][0], ha[0][1], hb[0][1], bA.x, bA.y);
                     mma16816(d, ha[0][2], hb[0][2], ha[0][3], hb[0][3], bA.z, bA.w);
                     mma16816(d, ha[1][0], hb[1][0], ha[1][1], hb[1][1], bB.x, bB.y);
                     mma16816(d, ha[1][2], hb[1][2], ha[1][3], hb[1][3], bB.z, bB.w);
-                    acc[ct][0] = fmaf(am0, d[0], acc[ct][0]);
-                    acc[ct][1] = fmaf(am0, d[1], acc[ct][1]);
-                    acc[ct][2] = fmaf(am1, d[2], acc[ct][2]);
-                    acc[ct][3] = fmaf(am1, d[3], acc[ct][3]);
+                    acc.v[ct][0] = fmaf(am0, d[0], acc.v[ct][0]);
+                    acc.v[ct][1] = fmaf(am0, d[1], acc.v[ct][1]);
+                    acc.v[ct][2] = fmaf(am1, d[2], acc.v[ct][2]);
+                    acc.v[ct][3] = fmaf(am1, d[3], acc.v[ct][3]);
                 }
-                ++kb;
-                bsrc += bstep;
-                if (kb == nkb || s + 1 == n) {
-                    flush(kb);
-                    if (kb == nkb) {
-                        kb = 0;
-                        ++tile;
-                        bsrc = sB + t;
-                    }
-                    seg_start_kb = kb;
+                bsaddr += bstep;
+                if (++kb == nkb) {  // row tile complete (for this warp's part of it)
+                    flush_tile<T, NCOLT>(fc, acc, tile, seg_start_kb, kb);
+#pragma unroll
+                    for (int c = 0; c < NCOLT; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc.v[c][i] = 0.f;
+                    kb = 0;
+                    seg_start_kb = 0;
+                    ++tile;
+                    bsaddr = sB_base;
                 }
             }
         }
+        if (FULL) {
+            if (fast) {
+                ld_left -= 4;
+                ld_ptr += 128;
+                if ((ld_kb += 4) == nkb) {
+                    ld_kb = 0;
+                    ld_ptr += tile_skip;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) load_unit(q0[u], q1[u]);
+            }
+        }
+    };
+
+    uint32_t s = 0;
+    for (; s + 8 <= n; s += 8) {
+        consume_group(qa0, qa1, std::true_type{}, 4);
+        consume_group(qb0, qb1, std::true_type{}, 4);
     }
+    const uint32_t rem = n - s;  // < 8 units left, already in the two register groups
+    if (rem) consume_group(qa0, qa1, std::false_type{}, rem < 4 ? rem : 4);
+    if (rem > 4) consume_group(qb0, qb1, std::false_type{}, rem - 4);
+#ifdef FP4_GEMV_TIMELINE
+    tl[3] = clock64();
+#endif
+    if (kb != seg_start_kb) flush_tile<T, NCOLT>(fc, acc, tile, seg_start_kb, kb);
+#ifdef FP4_GEMV_TIMELINE
+    tl[4] = clock64();
+    if (lane == 0) {
+        long long* dbg = reinterpret_cast<long long*>(ws.partials + (size_t)W * 2 * 16 * NC) + (size_t)wid * 8;
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        for (int i = 0; i < 5; ++i) dbg[i] = tl[i];
+        dbg[5] = smid;
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[6] = gt;
+    }
+#endif
 }
 
 struct Plan {
@@ -443,8 +609,15 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     ws.counters = reinterpret_cast<unsigned*>(workspace);
     ws.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
                                            kCounterBytes);
+    const uint32_t Wn = (uint32_t)grid * kWarps, Bn = (uint32_t)units;
+    Partition part;
+    part.q = Bn / Wn;
+    part.r = Bn % Wn;
+    part.by_q = FastDiv(part.q ? part.q : 1);
+    part.by_q1 = FastDiv(part.q + 1);
     kern<<<(unsigned)grid, kThreads, smem, st>>>((const T*)x, packed, absmax, nd, (const T*)bias,
-                                                 (T*)out, ws, batch, N, K, bs_log2 - 6);
+                                                 (T*)out, ws, batch, N, K, bs_log2 - 6, part,
+                                                 FastDiv((uint32_t)(K / 64)));
     return (int)cudaGetLastError();
 }
 
