@@ -64,7 +64,9 @@ enum {
        is honoured entry by entry through the generic kernel. */
     FP4_B200_FLAG_CODE_IS_BNB_FP4 = 1,
     /* force the generic CUDA-core GEMV (testing / A-B timing) */
-    FP4_B200_FLAG_FORCE_GENERIC = 2
+    FP4_B200_FLAG_FORCE_GENERIC = 2,
+    /* do not use the TMA-staged GEMV; take the register-streamed tensor-core GEMV (testing / A-B timing) */
+    FP4_B200_FLAG_NO_TMA = 4
 };
 
 /* nested ("double-quantised") absmax, bitsandbytes QuantState.state2 + offset:

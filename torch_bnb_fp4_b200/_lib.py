@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libfp4_b200.so")
 F16, F32, BF16 = 0, 1, 2
 FLAG_CODE_IS_BNB_FP4 = 1
 FLAG_FORCE_GENERIC = 2
+FLAG_NO_TMA = 4
 
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
