@@ -66,7 +66,9 @@ enum {
     /* force the generic CUDA-core GEMV (testing / A-B timing) */
     FP4_B200_FLAG_FORCE_GENERIC = 2,
     /* do not use the TMA-staged GEMV; take the register-streamed tensor-core GEMV (testing / A-B timing) */
-    FP4_B200_FLAG_NO_TMA = 4
+    FP4_B200_FLAG_NO_TMA = 4,
+    /* do not use the integer tensor-core GEMV (IMMA u8 x s8); take the fp16 tensor-core kernels (testing / A-B timing) */
+    FP4_B200_FLAG_NO_I8 = 8
 };
 
 /* nested ("double-quantised") absmax, bitsandbytes QuantState.state2 + offset:

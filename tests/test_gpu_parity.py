@@ -129,7 +129,7 @@ def _gemv_case(cuda, dtype, N, K, batch, bs=64, seed=0, bias=False, flags=0, cod
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N,K", [(256, 256), (64, 2048), (2048, 768), (1024, 4096), (48, 14336), (4096, 4096)])
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_I8, _lib.FLAG_FORCE_GENERIC])
 def test_gemv_batch1_vs_fp64_oracle(cuda, dtype, N, K, flags):
     y, exact, _ = _gemv_case(cuda, dtype, N, K, 1, seed=N + K, flags=flags)
     assert y.shape == (1, N) and y.dtype == dtype
@@ -138,7 +138,7 @@ def test_gemv_batch1_vs_fp64_oracle(cuda, dtype, N, K, flags):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("batch", [2, 3, 4, 5, 7, 8])
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_I8, _lib.FLAG_FORCE_GENERIC])
 def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
     y, exact, _ = _gemv_case(cuda, dtype, 512, 1024, batch, seed=batch, bias=True, flags=flags)
     assert y.shape == (batch, 512)

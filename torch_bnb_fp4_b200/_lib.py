@@ -12,6 +12,7 @@ F16, F32, BF16 = 0, 1, 2
 FLAG_CODE_IS_BNB_FP4 = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_NO_TMA = 4
+FLAG_NO_I8 = 8
 
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
