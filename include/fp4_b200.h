@@ -68,7 +68,9 @@ enum {
     /* do not use the TMA-staged GEMV; take the register-streamed tensor-core GEMV (testing / A-B timing) */
     FP4_B200_FLAG_NO_TMA = 4,
     /* do not use the integer tensor-core GEMV (IMMA u8 x s8); take the fp16 tensor-core kernels (testing / A-B timing) */
-    FP4_B200_FLAG_NO_I8 = 8
+    FP4_B200_FLAG_NO_I8 = 8,
+    /* do not use the default L2-prefetched streaming GEMV; take the stream-K kernels (testing / A-B timing) */
+    FP4_B200_FLAG_NO_STREAM = 16
 };
 
 /* nested ("double-quantised") absmax, bitsandbytes QuantState.state2 + offset:

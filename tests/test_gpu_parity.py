@@ -129,7 +129,8 @@ def _gemv_case(cuda, dtype, N, K, batch, bs=64, seed=0, bias=False, flags=0, cod
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N,K", [(256, 256), (64, 2048), (2048, 768), (1024, 4096), (48, 14336), (4096, 4096)])
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_I8, _lib.FLAG_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_STREAM, _lib.FLAG_NO_STREAM | _lib.FLAG_NO_I8,
+                                   _lib.FLAG_FORCE_GENERIC])
 def test_gemv_batch1_vs_fp64_oracle(cuda, dtype, N, K, flags):
     y, exact, _ = _gemv_case(cuda, dtype, N, K, 1, seed=N + K, flags=flags)
     assert y.shape == (1, N) and y.dtype == dtype
@@ -143,6 +144,28 @@ def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
     y, exact, _ = _gemv_case(cuda, dtype, 512, 1024, batch, seed=batch, bias=True, flags=flags)
     assert y.shape == (batch, 512)
     assert normwise(y.float().cpu().numpy(), exact) <= TOL64[dtype]
+
+
+# the default streaming kernel (whole row tiles per CTA, K % 512 == 0): ragged tile counts (150 tiles on
+# 148 CTAs), warps that straddle tiles (upt = 1, 3, 7), every batch size / MMA column-tile count
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,K,batch", [(2400, 512, 1), (1024, 1536, 2), (2368, 3584, 1), (1600, 1024, 3),
+                                       (1024, 1024, 4), (1024, 512, 5), (1024, 1024, 8), (4736, 512, 2)])
+def test_gemv_stream_kernel_shapes(cuda, dtype, N, K, batch):
+    if dtype == torch.float32 and batch > 4:
+        batch = 4  # fp32 activations take 4 integer terms: the kernel covers batch <= 4, beyond that stream-K
+    y, exact, _ = _gemv_case(cuda, dtype, N, K, batch, seed=N + K + batch, bias=(batch % 2 == 0))
+    assert y.shape == (batch, N)
+    assert normwise(y.float().cpu().numpy(), exact) <= TOL64[dtype]
+
+
+def test_gemv_stream_kernel_is_deterministic_and_matches_stream_k(cuda):
+    N, K = 4096, 4096
+    y0, exact, _ = _gemv_case(cuda, torch.bfloat16, N, K, 1, seed=5)
+    y1, _, _ = _gemv_case(cuda, torch.bfloat16, N, K, 1, seed=5)
+    assert torch.equal(y0, y1)
+    y2, _, _ = _gemv_case(cuda, torch.bfloat16, N, K, 1, seed=5, flags=_lib.FLAG_NO_STREAM)
+    assert normwise(y0.float().cpu().numpy(), y2.float().cpu().numpy().astype(np.float64)) <= 4e-3
 
 
 def test_gemv_custom_code_is_honoured(cuda):

@@ -13,6 +13,7 @@ FLAG_CODE_IS_BNB_FP4 = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_NO_TMA = 4
 FLAG_NO_I8 = 8
+FLAG_NO_STREAM = 16
 
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",

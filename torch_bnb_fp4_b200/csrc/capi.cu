@@ -23,6 +23,10 @@ bool gemv_i8_supported(int batch, int N, int K, int blocksize, int dtype, bool n
                        const void* packed, const void* absmax);
 int gemv_i8_dispatch(const void*, const uint8_t*, const float*, const void*, void*, void*, size_t, int,
                      int, int, int, cudaStream_t);
+bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested,
+                           const void* packed, const void* absmax);
+int gemv_stream_dispatch(const void*, const uint8_t*, const float*, const void*, void*, int, int, int, int,
+                         cudaStream_t);
 int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float*, const void*,
                           void*, int, int, int, int, int, unsigned, cudaStream_t);
 }  // namespace fp4b200
@@ -97,7 +101,12 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
     if (std_code && !(flags & FP4_B200_FLAG_FORCE_GENERIC) && workspace &&
         gemv_imma_supported(batch, N, K, blocksize, dtype)) {
         if (workspace_bytes < gemv_imma_workspace_bytes(N)) return FP4_B200_ERR_WORKSPACE;
-        // integer tensor-core kernel (TMA-staged) where its layout requirements hold
+        // default: L2-prefetched register-streamed integer tensor-core kernel (whole row tiles per CTA)
+        if (!(flags & FP4_B200_FLAG_NO_STREAM) &&
+            gemv_stream_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
+            return gemv_stream_dispatch(x, packed, absmax, bias, out, batch, N, K, dtype,
+                                        (cudaStream_t)stream);
+        // stream-K integer tensor-core kernel (TMA-staged) where its layout requirements hold
         if (!(flags & FP4_B200_FLAG_NO_I8) &&
             gemv_i8_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
             return gemv_i8_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch, N,

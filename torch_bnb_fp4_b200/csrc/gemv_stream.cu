@@ -1,0 +1,499 @@
+// Fused dequant + GEMV for decode (batch 1..8) on sm_100a — the default kernel for bitsandbytes-FP4
+// weights with blocksize 64:
+//
+//   out[b, r] = T( sum_k x[b,k] * code[W[r,k]] * absmax[r, k/64] + bias[r] )
+//
+// replaces the reference's gemv_4bit_inference kernels (csrc/gemv_fp4_optimized.cu:60-259).
+//
+// Memory side (what bounds the kernel).  One persistent CTA per SM owns a contiguous range of 16-row
+// tiles; its 8 warps split the range's units (16 rows x 512 k = 4 KiB of packed weights) contiguously.
+// Weights go HBM -> L2 -> registers: every warp keeps `pf` units of its own range in flight as L2
+// prefetches (no registers, no shared memory: the 126 MB L2 is the staging ring) and one unit in flight
+// as 128-bit register loads laid out directly in MMA-fragment order.  The prefetches and the first unit
+// are issued BEFORE griddepcontrol.wait, so under programmatic dependent launch the next layer's
+// weights stream into L2 while the current layer is still computing: HBM does not idle across the
+// launch boundary.
+//
+// Arithmetic side (must stay under ~20 issue slots per 8 weights to keep up with HBM):
+//   * weights: 192*|code| = {0,1,128,192,64,96,32,48} fits a byte: one PRMT against that 8-entry table
+//     turns four nibbles into four u8 magnitudes (ALL); a PRMT in sign-replicate mode gives 0x00/0xFF
+//     sign masks, ALL & mask = the magnitudes of the negative weights (NEG).
+//   * x: per (batch row, 64-block) a power-of-two scale, then x*s = t1 + t2/128 (+ t3/128^2 + t4/128^3
+//     for fp32) with s8 integers t_j (exact residual expansion, 2^-14 / 2^-28 of the block maximum).
+//   * sum_k w*x = absmax * 2^-e/192 * (IMMA(ALL,t) - 2 IMMA(NEG,t)): exact integer dot products on the
+//     tensor cores (mma.sync m16n8k32 u8 x s8), scaled once per (row, 64-block) in fp32.
+//   * one lane holds 16 contiguous bytes of a row (LDG.128), so the four lanes of an MMA k-group span
+//     TWO absmax blocks.  The B operand separates them: each (batch row, term) owns two MMA columns,
+//     one holding x for the lanes of block A and zeros elsewhere, the other the same for block B.
+//   The contraction is unchanged (one weight row x one activation vector); the tensor core is only the
+//   multiply-add engine that takes the FMAs off the issue-limited pipes.
+//
+// Row tiles are never split between CTAs (no global atomics, fences or workspace): tiles a CTA's warps
+// share are summed through shared memory in warp order after one __syncthreads (deterministic).
+//
+// Requirements (gemv_stream_supported): bitsandbytes FP4 codebook, blocksize 64, fp32 absmax,
+// K % 512 == 0, N % 16 == 0, enough row tiles to occupy the GPU, x terms fit in shared memory.
+#include <cstdlib>
+
+#include "gemv_common.cuh"
+
+namespace fp4b200 {
+namespace {
+
+using gemv::FastDiv;
+using gemv::XLoad;
+using gemv::lds_u2;
+using gemv::lds_u4;
+
+constexpr int kW = 8;  // warps per CTA
+constexpr int kThreads = kW * 32;
+constexpr float kMagic = 12582912.f;     // 1.5 * 2^23: int32 accumulators that start at its bit pattern read as floats
+constexpr uint32_t kTabHi = 0x30206040u;  // 192*|code[4..7]| = 64, 96, 32, 48  (low half 0xC0800100 lives in a register)
+constexpr uint32_t kZeroBytes = 512;      // zero region read by the lanes of masked MMA columns
+constexpr uint32_t kMaxSmem = 100 * 1024; // two launches (this layer + the prefetching next one) share an SM
+
+struct Params {
+    const void* x;
+    const uint8_t* packed;
+    const float* absmax;
+    const void* bias;
+    void* out;
+    int batch, N, K;
+    uint32_t upt;     // units per row tile = K / 512
+    uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
+    uint32_t pf;      // L2 prefetch distance in units (per warp)
+    FastDiv by_upt;
+};
+
+__device__ __forceinline__ void imma_first(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           uint32_t b0, uint32_t b1, int c) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c));
+}
+__device__ __forceinline__ void imma_acc(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One 32-bit word = 8 nibbles -> u8 magnitudes of nibbles 0..3 / 4..7 (ALL) and the same with the
+// non-negative weights zeroed (NEG).  Byte j of *_lo is nibble j, i.e. element (j ^ 1) of the word.
+__device__ __forceinline__ void decode_word(uint32_t w, uint32_t tab_lo, uint32_t& all_lo, uint32_t& all_hi,
+                                            uint32_t& neg_lo, uint32_t& neg_hi) {
+    const uint32_t wm = w & 0x77777777u;
+    const uint32_t w4 = w * 16u;  // integer multiply: issues on the FMA pipe, not the busier ALU pipe
+    all_lo = prmt(tab_lo, kTabHi, wm);
+    all_hi = prmt(tab_lo, kTabHi, __umulhi(wm, 65536u));
+    // sign-replicate mode (selector msb): byte = 0xFF if the selected source byte has its msb set
+    neg_lo = all_lo & prmt(w, w4, 0x9D8Cu);  // signs of nibbles 0,1,2,3
+    neg_hi = all_hi & prmt(w, w4, 0xBFAEu);  // signs of nibbles 4,5,6,7
+}
+
+__device__ __forceinline__ uint4 ldg_cached_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+#ifndef FP4_STREAM_MINB
+#define FP4_STREAM_MINB 2
+#endif
+template <typename T, int NCT>
+__global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) gemv_stream_kernel(const __grid_constant__ Params p) {
+    constexpr int TERMS = sizeof(T) == 4 ? 4 : 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t g = lane >> 2, t = lane & 3;
+    const int batch = p.batch, nq = batch * TERMS;
+    const uint32_t K = (uint32_t)p.K, nkb = K >> 6, rowb = K >> 1;  // rowb: packed bytes per weight row
+
+    // ---- shared memory carve-up -----------------------------------------------------------------
+    uint8_t* sX = smem;                                   // [nq][K] s8, pairs of k swapped (nibble order)
+    uint8_t* sZero = sX + (size_t)nq * K;                 // kZeroBytes of zeros
+    float* sXs = reinterpret_cast<float*>(sZero + kZeroBytes);  // [batch][nkb] 2^-e / 192
+    float* sPart = sXs + (size_t)batch * nkb;             // [kW][2][batch*16]
+
+    // ---- this CTA's tiles and this warp's units ----------------------------------------------------
+    const uint32_t cta = blockIdx.x;
+    const uint32_t tile0 = cta * p.tq + (cta < p.tr ? cta : p.tr);
+    const uint32_t ntile = p.tq + (cta < p.tr ? 1u : 0u);
+    const uint32_t nU = ntile * p.upt;
+    const uint32_t wq = nU / kW, wr = nU % kW;
+    const uint32_t ua = (uint32_t)warp * wq + ((uint32_t)warp < wr ? (uint32_t)warp : wr);  // first unit (CTA-local)
+    const uint32_t n = wq + ((uint32_t)warp < wr ? 1u : 0u);
+    uint32_t tl_a, ku_a;  // CTA-local tile and unit-in-tile of the first unit
+    p.by_upt.divmod(ua, tl_a, ku_a);
+
+    // loader: lane (g, t) reads 16 B of row g and 16 B of row g + 8 per 128-k step; 4 steps per unit
+    const size_t trow = (size_t)(tile0 + tl_a) * 16;
+    const uint8_t* wp = p.packed + (trow + g) * rowb + ku_a * 256 + t * 16;
+    const uint32_t row8 = 8 * rowb;
+    // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds 4 of them: row g + 8 (t & 1), blocks 4 (t >> 1) ..
+    const float* ap = p.absmax + (trow + g + 8 * (t & 1)) * nkb + ku_a * 8 + 4 * (t >> 1);
+    uint32_t ld_ku = ku_a;
+    // L2 prefetcher: lane l covers 128 B of row l >> 1 of a unit; lanes < 16 also one row of its absmax
+    const uint8_t* pfw = p.packed + (trow + (lane >> 1)) * rowb + ku_a * 256 + (lane & 1) * 128;
+    const float* pfa = p.absmax + (trow + (lane & 15)) * nkb + ku_a * 8;
+    uint32_t pf_ku = ku_a, pf_left = n;
+    auto prefetch_unit = [&]() {
+        prefetch_l2(pfw);
+        if (lane < 16) prefetch_l2(pfa);
+        if (++pf_ku == p.upt) {
+            pf_ku = 0;
+            pfw += 256 + 15 * (size_t)rowb;
+            pfa += 8 + 15 * (size_t)nkb;
+        } else {
+            pfw += 256;
+            pfa += 8;
+        }
+        --pf_left;
+    };
+
+    uint4 wb[4][2];  // the unit being consumed / refilled step by step with the next one
+    uint4 amn;       // absmax of the next unit
+    // ---- 1. start the weight stream: nothing here depends on the previous kernel in the stream -----
+    if (n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wb[j][0] = ldg_stream_u4(wp + j * 64);
+            wb[j][1] = ldg_stream_u4(wp + j * 64 + row8);
+        }
+        amn = ldg_cached_u4(ap);
+        prefetch_unit();  // unit 0 itself is already being loaded; keeps the prefetcher one ahead
+        for (uint32_t i = 0; i < p.pf && pf_left; ++i) prefetch_unit();
+    }
+    // x and `out` may be products of the previous kernel: wait for it, then let the next kernel start
+    // its own prologue (its prefetches run while this kernel computes)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+
+    // ---- 2. stage x as s8 residual terms, one power-of-two scale per (batch row, 64-block) ----------
+    for (uint32_t i = tid; i < kZeroBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sZero)[i] = 0u;
+    {
+        const T* x = reinterpret_cast<const T*>(p.x);
+        const int nchunk = (int)(K >> 3);
+        for (int b = 0; b < batch; ++b) {
+            for (int c = tid; c < nchunk; c += kThreads) {
+                float f[8];
+                XLoad<T>::load(x + (size_t)b * K + c * 8, f);
+                float mx = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[i]));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                uint32_t E = (__float_as_uint(mx) >> 23) & 0xFFu;
+                E = E < 32u ? 32u : (E > 250u ? 250u : E);
+                const float s = __uint_as_float((259u - E) << 23);  // 2^(5 - e): |x * s| < 64
+                if ((c & 7) == 0) sXs[b * nkb + (c >> 3)] = __uint_as_float((E - 5u) << 23) * (1.f / 192.f);
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = f[i] * s;
+                uint8_t* dst = sX + (size_t)(b * TERMS) * K + (size_t)c * 8;
+#pragma unroll
+                for (int j = 0; j < TERMS; ++j) {
+                    uint32_t ti[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float rr = y[i] + kMagic;  // round to nearest integer
+                        ti[i] = __float_as_uint(rr);
+                        if (j + 1 < TERMS) y[i] = (y[i] - (rr - kMagic)) * 128.f;  // exact residual, rescaled
+                    }
+                    // byte order = nibble order of the packed weights: (k+1, k, k+3, k+2)
+                    const uint32_t w0 = prmt(prmt(ti[1], ti[0], 0x0040u), prmt(ti[3], ti[2], 0x0040u), 0x5410u);
+                    const uint32_t w1 = prmt(prmt(ti[5], ti[4], 0x0040u), prmt(ti[7], ti[6], 0x0040u), 0x5410u);
+                    *reinterpret_cast<uint2*>(dst + (size_t)j * K) = make_uint2(w0, w1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. main loop over this warp's units --------------------------------------------------------
+    // B fragments: MMA column ct*8 + g = ((batch row, term) q, block blk); lanes of the other block's
+    // k-group read zeros
+    uint32_t xbase[NCT], xstep[NCT], sbase[NCT];
+    const uint32_t sX_a = (uint32_t)__cvta_generic_to_shared(sX);
+    const uint32_t sZero_a = (uint32_t)__cvta_generic_to_shared(sZero);
+    const uint32_t sXs_a = (uint32_t)__cvta_generic_to_shared(sXs);
+#pragma unroll
+    for (int ct = 0; ct < NCT; ++ct) {
+        const int col = ct * 8 + (int)g, q = col >> 1, blk = col & 1;
+        const bool valid = q < nq && (int)(t >> 1) == blk;
+        xbase[ct] = valid ? sX_a + (uint32_t)q * K + t * 32 : sZero_a + 16;
+        xstep[ct] = valid ? 512u : 0u;  // bytes per unit
+        int qs = ct * 4 + (int)t;       // the (batch row, term) whose two columns this lane reads back
+        qs = qs < nq ? qs : 0;
+        sbase[ct] = sXs_a + (uint32_t)(qs / TERMS) * nkb * 4;
+    }
+    uint32_t tab_lo;
+    asm volatile("mov.b32 %0, 0xC0800100;" : "=r"(tab_lo));  // 192*|code[0..3]| = 0, 1, 128, 192
+    int magic_i;
+    asm volatile("mov.b32 %0, 0x4B400000;" : "=r"(magic_i));
+    const uint32_t quad = lane & 28u;
+
+    float acc[NCT][2];  // rows g, g + 8 of (batch row, term) ct*4 + t
+#pragma unroll
+    for (int ct = 0; ct < NCT; ++ct) acc[ct][0] = acc[ct][1] = 0.f;
+
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    T* out = reinterpret_cast<T*>(p.out);
+    float* myPart = sPart + (size_t)warp * 2 * batch * 16;
+
+    // finish this warp's share (cnt units) of CTA-local tile tl
+    auto flush = [&](uint32_t tl, uint32_t cnt) {
+        const uint32_t row0 = (tile0 + tl) * 16;
+        const bool whole = cnt == p.upt;
+        float* part = myPart + (tl == tl_a ? 0 : batch * 16);
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) {
+            float v0 = acc[ct][0], v1 = acc[ct][1];
+            acc[ct][0] = acc[ct][1] = 0.f;
+            int b;
+            bool owner;
+            if constexpr (TERMS == 2) {
+                const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1), o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+                v0 = fmaf(o0, 1.f / 128.f, v0);
+                v1 = fmaf(o1, 1.f / 128.f, v1);
+                owner = (t & 1) == 0;
+                b = ct * 2 + (int)(t >> 1);
+            } else {
+                const float wgt = t == 0 ? 1.f : t == 1 ? (1.f / 128.f) : t == 2 ? (1.f / 16384.f) : (1.f / 2097152.f);
+                v0 *= wgt;
+                v1 *= wgt;
+                v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                owner = t == 0;
+                b = ct;
+            }
+            if (owner && b < batch) {
+                if (whole) {
+                    const uint32_t r0 = row0 + g, r1 = r0 + 8;
+                    if (bias) {
+                        v0 += DT<T>::to_f32(bias[r0]);
+                        v1 += DT<T>::to_f32(bias[r1]);
+                    }
+                    out[(size_t)b * p.N + r0] = DT<T>::from_f32(v0);
+                    out[(size_t)b * p.N + r1] = DT<T>::from_f32(v1);
+                } else {
+                    part[b * 16 + g] = v0;
+                    part[b * 16 + g + 8] = v1;
+                }
+            }
+        }
+    };
+
+    uint32_t tl = tl_a, ku = ku_a, cnt = 0;
+    for (uint32_t left = n; left; --left) {
+        const bool more = left > 1;
+        const uint4 amc = amn;
+        if (more) {  // advance the loader to the next unit
+            if (++ld_ku == p.upt) {
+                ld_ku = 0;
+                wp += 256 + 15 * (size_t)rowb;
+                ap += 8 + 15 * (size_t)nkb;
+            } else {
+                wp += 256;
+                ap += 8;
+            }
+            amn = ldg_cached_u4(ap);
+        }
+        if (pf_left) prefetch_unit();
+        uint32_t xa[NCT], sa[NCT];
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) {
+            xa[ct] = xbase[ct] + ku * xstep[ct];
+            sa[ct] = sbase[ct] + ku * 32;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t wA[4] = {wb[j][0].x, wb[j][0].y, wb[j][0].z, wb[j][0].w};
+            const uint32_t wB[4] = {wb[j][1].x, wb[j][1].y, wb[j][1].z, wb[j][1].w};
+            // absmax of blocks (2j, 2j+1) of rows g / g+8 sit in lanes t = 2(j>>1) / 2(j>>1)+1 of the quad
+            const uint32_t srcA = quad | (2 * (j >> 1)), srcB = srcA + 1;
+            const uint32_t c0 = (j & 1) ? amc.z : amc.x, c1 = (j & 1) ? amc.w : amc.y;
+            const float amA0 = __uint_as_float(__shfl_sync(0xffffffffu, c0, srcA));
+            const float amA1 = __uint_as_float(__shfl_sync(0xffffffffu, c1, srcA));
+            const float amB0 = __uint_as_float(__shfl_sync(0xffffffffu, c0, srcB));
+            const float amB1 = __uint_as_float(__shfl_sync(0xffffffffu, c1, srcB));
+            int dall[NCT][4], dneg[NCT][4];
+            uint4 bx01 = make_uint4(0, 0, 0, 0), bx23 = bx01;
+            if constexpr (NCT == 1) {
+                bx01 = lds_u4(xa[0] + j * 128);
+                bx23 = lds_u4(xa[0] + j * 128 + 16);
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                uint32_t aA0, aA1, nA0, nA1, aB0, aB1, nB0, nB1;
+                decode_word(wA[m], tab_lo, aA0, aA1, nA0, nA1);
+                decode_word(wB[m], tab_lo, aB0, aB1, nB0, nB1);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    uint2 bx;
+                    if constexpr (NCT == 1) {  // two 128-bit loads per step (conflict-free: a quarter-warp reads one x row)
+                        bx = m == 0 ? make_uint2(bx01.x, bx01.y) : m == 1 ? make_uint2(bx01.z, bx01.w)
+                           : m == 2 ? make_uint2(bx23.x, bx23.y) : make_uint2(bx23.z, bx23.w);
+                    } else {
+                        bx = lds_u2(xa[ct] + j * 128 + m * 8);
+                    }
+                    if (m == 0) {
+                        imma_first(dall[ct], aA0, aB0, aA1, aB1, bx.x, bx.y, magic_i);
+                        imma_first(dneg[ct], nA0, nB0, nA1, nB1, bx.x, bx.y, magic_i);
+                    } else {
+                        imma_acc(dall[ct], aA0, aB0, aA1, aB1, bx.x, bx.y);
+                        imma_acc(dneg[ct], nA0, nB0, nA1, nB1, bx.x, bx.y);
+                    }
+                }
+            }
+            if (more) {  // the words are decoded: refill the registers with the next unit's step j
+                wb[j][0] = ldg_stream_u4(wp + j * 64);
+                wb[j][1] = ldg_stream_u4(wp + j * 64 + row8);
+            }
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct) {
+                const uint2 xs = lds_u2(sa[ct] + j * 8);
+                const float xs0 = __uint_as_float(xs.x), xs1 = __uint_as_float(xs.y);
+                // both accumulators started at the bit pattern of 1.5*2^23, so as floats they read
+                // 1.5*2^23 + sum exactly; (M + all) - 2 (M + neg) + M = all - 2 neg, every step exact
+                const float f0 = fmaf(__int_as_float(dneg[ct][0]), -2.f, __int_as_float(dall[ct][0])) + kMagic;
+                const float f1 = fmaf(__int_as_float(dneg[ct][1]), -2.f, __int_as_float(dall[ct][1])) + kMagic;
+                const float f2 = fmaf(__int_as_float(dneg[ct][2]), -2.f, __int_as_float(dall[ct][2])) + kMagic;
+                const float f3 = fmaf(__int_as_float(dneg[ct][3]), -2.f, __int_as_float(dall[ct][3])) + kMagic;
+                acc[ct][0] = fmaf(f0, amA0 * xs0, acc[ct][0]);
+                acc[ct][0] = fmaf(f1, amA1 * xs1, acc[ct][0]);
+                acc[ct][1] = fmaf(f2, amB0 * xs0, acc[ct][1]);
+                acc[ct][1] = fmaf(f3, amB1 * xs1, acc[ct][1]);
+            }
+        }
+        ++cnt;
+        if (++ku == p.upt || !more) {
+            flush(tl, cnt);
+            ++tl;
+            ku = 0;
+            cnt = 0;
+        }
+    }
+
+    // ---- 4. tiles shared between warps: sum the parked partials in warp order ------------------------
+    __syncthreads();
+    {
+        const uint32_t per = 16u * (uint32_t)batch;
+        const uint32_t big = wr * (wq + 1);
+        auto unit_owner = [&](uint32_t u) { return u < big ? u / (wq + 1) : wr + (u - big) / (wq ? wq : 1u); };
+        for (uint32_t idx = tid; idx < ntile * per; idx += kThreads) {
+            const uint32_t tt = idx / per, e = idx - tt * per;
+            const uint32_t wa = unit_owner(tt * p.upt), wz = unit_owner(tt * p.upt + p.upt - 1);
+            if (wa == wz) continue;  // one warp covered the whole tile and stored it
+            float v = 0.f;
+            for (uint32_t w = wa; w <= wz; ++w) {
+                const uint32_t w_ua = w * wq + (w < wr ? w : wr);
+                const uint32_t w_tl = p.by_upt.div(w_ua);
+                v += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e];
+            }
+            const uint32_t row = (tile0 + tt) * 16 + (e & 15), b = e >> 4;
+            if (bias) v += DT<T>::to_f32(bias[row]);
+            out[(size_t)b * p.N + row] = DT<T>::from_f32(v);
+        }
+    }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int nterms(int dtype) { return dtype == FP4_B200_F32 ? 4 : 2; }
+
+static size_t smem_bytes(int batch, int K, int nt) {
+    return (size_t)batch * nt * K + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
+}
+
+template <typename T, int NCT>
+static int launch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
+                  int batch, int N, int K, cudaStream_t st) {
+    auto kern = gemv_stream_kernel<T, NCT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    static const int use_pdl = env_int("FP4_B200_GEMV_PDL", 1);
+    static const int pf = env_int("FP4_B200_GEMV_PF", 0);
+    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", 2);
+    const uint32_t tiles = (uint32_t)N / 16;
+    const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
+    const uint32_t grid = tiles < max_grid ? tiles : max_grid;
+    Params p;
+    p.x = x; p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;
+    p.batch = batch; p.N = N; p.K = K;
+    p.upt = (uint32_t)K / 512;
+    p.tq = tiles / grid; p.tr = tiles % grid;
+    p.pf = (uint32_t)(pf < 0 ? 0 : pf);
+    p.by_upt = FastDiv(p.upt);
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes(batch, K, sizeof(T) == 4 ? 4 : 2);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T, int NT>
+static int launch_nct(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
+                      int batch, int N, int K, cudaStream_t st) {
+    const int nct = (batch * NT * 2 + 7) / 8;
+#define FP4_GO(NCT) launch<T, NCT>(x, packed, absmax, bias, out, batch, N, K, st)
+    if (nct <= 1) return FP4_GO(1);
+    if (nct <= 2) return FP4_GO(2);
+    return FP4_GO(4);
+#undef FP4_GO
+}
+
+}  // namespace
+
+bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested, const void* packed,
+                           const void* absmax) {
+    static const int disabled = env_int("FP4_B200_GEMV_NO_STREAM", 0);
+    static const int min_tiles = env_int("FP4_B200_GEMV_STREAM_MIN_TILES", 48);
+    if (disabled || nested || blocksize != 64) return false;
+    if (batch < 1 || batch > 8 || N <= 0 || K <= 0) return false;
+    if (K % 512 != 0 || N % 16 != 0) return false;
+    if (N / 16 < min_tiles) return false;  // too few row tiles to occupy the GPU: the stream-K kernels split K
+    if ((uint64_t)N * (uint64_t)K >= (1ull << 40)) return false;
+    if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(absmax) % 16) return false;
+    const int nt = nterms(dtype);
+    if ((batch * nt * 2 + 7) / 8 > 4) return false;
+    return smem_bytes(batch, K, nt) <= kMaxSmem;
+}
+
+int gemv_stream_dispatch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
+                         int batch, int N, int K, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case FP4_B200_F16:
+            return launch_nct<__half, 2>(x, packed, absmax, bias, out, batch, N, K, st);
+        case FP4_B200_BF16:
+            return launch_nct<__nv_bfloat16, 2>(x, packed, absmax, bias, out, batch, N, K, st);
+        case FP4_B200_F32:
+            return launch_nct<float, 4>(x, packed, absmax, bias, out, batch, N, K, st);
+        default:
+            return FP4_B200_ERR_DTYPE;
+    }
+}
+
+}  // namespace fp4b200
