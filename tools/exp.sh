@@ -1,10 +1,12 @@
 set -x
 cd torch_bnb_fp4_b200
-touch csrc/gemv_i8.cu
-FP4_B200_NVCC_EXTRA="-DFP4_I8_NOCOMPUTE -DFP4_I8_TIMELINE" python build.py > /dev/null 2>&1
-export FP4_B200_GEMV_CTAS_PER_SM=1
-KW=16 python ../tools/i8_timeline.py 14336 4096 5 | tail -24
-python ../tools/i8_timeline.py 4096 4096 5 | tail -16
-touch csrc/gemv_i8.cu
-FP4_B200_NVCC_EXTRA="-DFP4_I8_TIMELINE" python build.py > /dev/null 2>&1
-python ../tools/i8_timeline.py 14336 4096 5 | tail -16
+touch csrc/gemv_stream.cu
+FP4_B200_NVCC_EXTRA="-DFP4_STREAM_WARPS=16 -DFP4_STREAM_MINB=2" python build.py > /dev/null 2>&1
+echo "=== WARPS=16 MINB=2 smem 112"
+FP4_B200_GEMV_SMEM_KB=112 python ../tools/microbench.py --batch 1 --no-dequant
+echo "=== WARPS=16 MINB=2 smem 226"
+python ../tools/microbench.py --batch 1 --no-dequant
+touch csrc/gemv_stream.cu
+FP4_B200_NVCC_EXTRA="-DFP4_STREAM_WARPS=16 -DFP4_STREAM_MINB=1" python build.py > /dev/null 2>&1
+echo "=== WARPS=16 MINB=1 smem 226"
+python ../tools/microbench.py --batch 1 --no-dequant

@@ -6,13 +6,15 @@
 // replaces the reference's gemv_4bit_inference kernels (csrc/gemv_fp4_optimized.cu:60-259).
 //
 // Memory side (what bounds the kernel).  One persistent CTA per SM owns a contiguous range of 16-row
-// tiles; its 8 warps split the range's units (16 rows x 512 k = 4 KiB of packed weights) contiguously.
-// Weights go HBM -> L2 -> registers: every warp keeps `pf` units of its own range in flight as L2
-// prefetches (no registers, no shared memory: the 126 MB L2 is the staging ring) and one unit in flight
-// as 128-bit register loads laid out directly in MMA-fragment order.  The prefetches and the first unit
-// are issued BEFORE griddepcontrol.wait, so under programmatic dependent launch the next layer's
-// weights stream into L2 while the current layer is still computing: HBM does not idle across the
-// launch boundary.
+// tiles; its 16 warps split the range's units (16 rows x 512 k = 4 KiB of packed weights + 512 B of
+// absmax) contiguously.  Loaded latency of HBM on B200 is ~2 us, so ~100+ KB per SM must be in flight:
+// far more than registers hold.  Every warp therefore owns a private ring of `ring` unit slots in shared
+// memory, filled with 16-byte cp.async copies laid out directly in MMA-fragment order (lane l's bytes
+// at lane l's slot: each lane reads back only what it copied, so there are no barriers, no bank
+// conflicts and no cross-lane visibility to wait for — cp.async.wait_group is the only
+// synchronisation).  The ring is filled BEFORE griddepcontrol.wait: under programmatic dependent
+// launch the next layer's first units are already on their way while the current layer finishes, and a
+// layer of <= 1 unit per warp (4096x4096) is entirely in flight before its input exists.
 //
 // Arithmetic side (must stay under ~20 issue slots per 8 weights to keep up with HBM):
 //   * weights: 192*|code| = {0,1,128,192,64,96,32,48} fits a byte: one PRMT against that 8-entry table
@@ -38,6 +40,10 @@
 #include "gemv_common.cuh"
 
 namespace fp4b200 {
+#ifdef FP4_STREAM_TIMELINE
+long long* g_stream_tl = nullptr;
+int g_stream_tl_launch = 0;
+#endif
 namespace {
 
 using gemv::FastDiv;
@@ -45,12 +51,20 @@ using gemv::XLoad;
 using gemv::lds_u2;
 using gemv::lds_u4;
 
-constexpr int kW = 8;  // warps per CTA
+#ifndef FP4_STREAM_MINB
+#define FP4_STREAM_MINB 1
+#endif
+#ifndef FP4_STREAM_WARPS
+#define FP4_STREAM_WARPS 16
+#endif
+constexpr int kW = FP4_STREAM_WARPS;  // warps per CTA
 constexpr int kThreads = kW * 32;
 constexpr float kMagic = 12582912.f;     // 1.5 * 2^23: int32 accumulators that start at its bit pattern read as floats
 constexpr uint32_t kTabHi = 0x30206040u;  // 192*|code[4..7]| = 64, 96, 32, 48  (low half 0xC0800100 lives in a register)
 constexpr uint32_t kZeroBytes = 512;      // zero region read by the lanes of masked MMA columns
-constexpr uint32_t kMaxSmem = 100 * 1024; // two launches (this layer + the prefetching next one) share an SM
+constexpr uint32_t kMaxSmem = 226 * 1024; // per CTA: half an SM, so the next launch (PDL) is resident while this one runs
+constexpr uint32_t kSlot = 4096 + 512;    // one unit: 4 steps x 2 row halves x 32 lanes x 16 B, then 32 lanes x 16 B of absmax
+constexpr uint32_t kMaxRing = 4;
 
 struct Params {
     const void* x;
@@ -61,9 +75,23 @@ struct Params {
     int batch, N, K;
     uint32_t upt;     // units per row tile = K / 512
     uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
-    uint32_t pf;      // L2 prefetch distance in units (per warp)
+    uint32_t ring;    // unit slots per warp (1..kMaxRing)
     FastDiv by_upt;
+    long long* tl;    // debug timeline (FP4_STREAM_TIMELINE builds): [cta][warp][8] globaltimer ns
 };
+
+#ifdef FP4_STREAM_TIMELINE
+#define TL_STAMP(i)                                                              \
+    do {                                                                         \
+        if (p.tl && lane == 0) {                                                 \
+            long long gt_;                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));              \
+            p.tl[((size_t)blockIdx.x * kW + warp) * 8 + (i)] = gt_;              \
+        }                                                                        \
+    } while (0)
+#else
+#define TL_STAMP(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ void imma_first(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                            uint32_t b0, uint32_t b1, int c) {
@@ -93,20 +121,24 @@ __device__ __forceinline__ void decode_word(uint32_t w, uint32_t tab_lo, uint32_
     neg_hi = all_hi & prmt(w, w4, 0xBFAEu);  // signs of nibbles 4,5,6,7
 }
 
-__device__ __forceinline__ uint4 ldg_cached_u4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
+__device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+__device__ __forceinline__ void cp_async_ca16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t pending) {  // uniform across the CTA
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
 }
 
-#ifndef FP4_STREAM_MINB
-#define FP4_STREAM_MINB 2
-#endif
 template <typename T, int NCT>
-__global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) gemv_stream_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(const __grid_constant__ Params p) {
     constexpr int TERMS = sizeof(T) == 4 ? 4 : 2;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -115,7 +147,8 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
     const uint32_t K = (uint32_t)p.K, nkb = K >> 6, rowb = K >> 1;  // rowb: packed bytes per weight row
 
     // ---- shared memory carve-up -----------------------------------------------------------------
-    uint8_t* sX = smem;                                   // [nq][K] s8, pairs of k swapped (nibble order)
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * p.ring * kSlot + lane * 16;
+    uint8_t* sX = smem + (size_t)kW * p.ring * kSlot;     // [nq][K] s8, pairs of k swapped (nibble order)
     uint8_t* sZero = sX + (size_t)nq * K;                 // kZeroBytes of zeros
     float* sXs = reinterpret_cast<float*>(sZero + kZeroBytes);  // [batch][nkb] 2^-e / 192
     float* sPart = sXs + (size_t)batch * nkb;             // [kW][2][batch*16]
@@ -137,42 +170,37 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
     const uint32_t row8 = 8 * rowb;
     // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds 4 of them: row g + 8 (t & 1), blocks 4 (t >> 1) ..
     const float* ap = p.absmax + (trow + g + 8 * (t & 1)) * nkb + ku_a * 8 + 4 * (t >> 1);
-    uint32_t ld_ku = ku_a;
-    // L2 prefetcher: lane l covers 128 B of row l >> 1 of a unit; lanes < 16 also one row of its absmax
-    const uint8_t* pfw = p.packed + (trow + (lane >> 1)) * rowb + ku_a * 256 + (lane & 1) * 128;
-    const float* pfa = p.absmax + (trow + (lane & 15)) * nkb + ku_a * 8;
-    uint32_t pf_ku = ku_a, pf_left = n;
-    auto prefetch_unit = [&]() {
-        prefetch_l2(pfw);
-        if (lane < 16) prefetch_l2(pfa);
-        if (++pf_ku == p.upt) {
-            pf_ku = 0;
-            pfw += 256 + 15 * (size_t)rowb;
-            pfa += 8 + 15 * (size_t)nkb;
-        } else {
-            pfw += 256;
-            pfa += 8;
-        }
-        --pf_left;
-    };
-
-    uint4 wb[4][2];  // the unit being consumed / refilled step by step with the next one
-    uint4 amn;       // absmax of the next unit
-    // ---- 1. start the weight stream: nothing here depends on the previous kernel in the stream -----
-    if (n) {
+    TL_STAMP(0);
+    uint32_t ld_ku = ku_a, issued = 0;
+    // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
+    auto issue_unit = [&](uint32_t dst) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            wb[j][0] = ldg_stream_u4(wp + j * 64);
-            wb[j][1] = ldg_stream_u4(wp + j * 64 + row8);
+            cp_async_cg16(dst + j * 1024, wp + j * 64);
+            cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
         }
-        amn = ldg_cached_u4(ap);
-        prefetch_unit();  // unit 0 itself is already being loaded; keeps the prefetcher one ahead
-        for (uint32_t i = 0; i < p.pf && pf_left; ++i) prefetch_unit();
+        cp_async_ca16(dst + 4096, ap);
+        if (++ld_ku == p.upt) {
+            ld_ku = 0;
+            wp += 256 + 15 * (size_t)rowb;
+            ap += 8 + 15 * (size_t)nkb;
+        } else {
+            wp += 256;
+            ap += 8;
+        }
+        ++issued;
+    };
+    // ---- 1. fill the ring: nothing here depends on the previous kernel in the stream ----------------
+    for (uint32_t r = 0; r < p.ring; ++r) {
+        if (issued < n) issue_unit(ring_a + r * kSlot);
+        cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
     }
+    TL_STAMP(1);
     // x and `out` may be products of the previous kernel: wait for it, then let the next kernel start
     // its own prologue (its prefetches run while this kernel computes)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    TL_STAMP(2);
 
     // ---- 2. stage x as s8 residual terms, one power-of-two scale per (batch row, 64-block) ----------
     for (uint32_t i = tid; i < kZeroBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sZero)[i] = 0u;
@@ -215,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
         }
     }
     __syncthreads();
+    TL_STAMP(3);
 
     // ---- 3. main loop over this warp's units --------------------------------------------------------
     // B fragments: MMA column ct*8 + g = ((batch row, term) q, block blk); lanes of the other block's
@@ -292,22 +321,15 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
         }
     };
 
-    uint32_t tl = tl_a, ku = ku_a, cnt = 0;
+    uint32_t tl = tl_a, ku = ku_a, cnt = 0, slot = 0;
     for (uint32_t left = n; left; --left) {
         const bool more = left > 1;
-        const uint4 amc = amn;
-        if (more) {  // advance the loader to the next unit
-            if (++ld_ku == p.upt) {
-                ld_ku = 0;
-                wp += 256 + 15 * (size_t)rowb;
-                ap += 8 + 15 * (size_t)nkb;
-            } else {
-                wp += 256;
-                ap += 8;
-            }
-            amn = ldg_cached_u4(ap);
-        }
-        if (pf_left) prefetch_unit();
+        cp_async_wait_pending(p.ring - 1);  // the oldest group (this unit) has landed
+#ifdef FP4_STREAM_TIMELINE
+        if (left == n) TL_STAMP(4);
+#endif
+        const uint32_t sl = ring_a + slot * kSlot;
+        const uint4 amc = lds_u4(sl + 4096);
         uint32_t xa[NCT], sa[NCT];
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
@@ -316,8 +338,9 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t wA[4] = {wb[j][0].x, wb[j][0].y, wb[j][0].z, wb[j][0].w};
-            const uint32_t wB[4] = {wb[j][1].x, wb[j][1].y, wb[j][1].z, wb[j][1].w};
+            const uint4 wA4 = lds_u4(sl + j * 1024), wB4 = lds_u4(sl + j * 1024 + 512);
+            const uint32_t wA[4] = {wA4.x, wA4.y, wA4.z, wA4.w};
+            const uint32_t wB[4] = {wB4.x, wB4.y, wB4.z, wB4.w};
             // absmax of blocks (2j, 2j+1) of rows g / g+8 sit in lanes t = 2(j>>1) / 2(j>>1)+1 of the quad
             const uint32_t srcA = quad | (2 * (j >> 1)), srcB = srcA + 1;
             const uint32_t c0 = (j & 1) ? amc.z : amc.x, c1 = (j & 1) ? amc.w : amc.y;
@@ -354,10 +377,6 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
                     }
                 }
             }
-            if (more) {  // the words are decoded: refill the registers with the next unit's step j
-                wb[j][0] = ldg_stream_u4(wp + j * 64);
-                wb[j][1] = ldg_stream_u4(wp + j * 64 + row8);
-            }
 #pragma unroll
             for (int ct = 0; ct < NCT; ++ct) {
                 const uint2 xs = lds_u2(sa[ct] + j * 8);
@@ -374,6 +393,10 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
                 acc[ct][1] = fmaf(f3, amB1 * xs1, acc[ct][1]);
             }
         }
+        // every word of the slot has been decoded: refill it with the unit `ring` ahead
+        if (issued < n) issue_unit(sl);
+        cp_async_commit();
+        slot = slot + 1 == p.ring ? 0 : slot + 1;
         ++cnt;
         if (++ku == p.upt || !more) {
             flush(tl, cnt);
@@ -384,7 +407,9 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
     }
 
     // ---- 4. tiles shared between warps: sum the parked partials in warp order ------------------------
+    TL_STAMP(5);
     __syncthreads();
+    TL_STAMP(6);
     {
         const uint32_t per = 16u * (uint32_t)batch;
         const uint32_t big = wr * (wq + 1);
@@ -404,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, (NCT == 1 ? FP4_STREAM_MINB : 2)) ge
             out[(size_t)b * p.N + row] = DT<T>::from_f32(v);
         }
     }
+    TL_STAMP(7);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -413,7 +439,7 @@ static int env_int(const char* name, int dflt) {
 
 static int nterms(int dtype) { return dtype == FP4_B200_F32 ? 4 : 2; }
 
-static size_t smem_bytes(int batch, int K, int nt) {
+static size_t fixed_smem_bytes(int batch, int K, int nt) {
     return (size_t)batch * nt * K + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
 }
 
@@ -428,23 +454,34 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
         configured = true;
     }
     static const int use_pdl = env_int("FP4_B200_GEMV_PDL", 1);
-    static const int pf = env_int("FP4_B200_GEMV_PF", 0);
-    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", 2);
+    static const int max_ring = env_int("FP4_B200_GEMV_RING", (int)kMaxRing);
     const uint32_t tiles = (uint32_t)N / 16;
-    const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
-    const uint32_t grid = tiles < max_grid ? tiles : max_grid;
+    const uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     Params p;
     p.x = x; p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;
     p.batch = batch; p.N = N; p.K = K;
     p.upt = (uint32_t)K / 512;
     p.tq = tiles / grid; p.tr = tiles % grid;
-    p.pf = (uint32_t)(pf < 0 ? 0 : pf);
     p.by_upt = FastDiv(p.upt);
+    // ring depth: no deeper than a warp has units, no larger than shared memory allows
+    const size_t fixed = fixed_smem_bytes(batch, K, sizeof(T) == 4 ? 4 : 2);
+    const uint32_t units_per_warp = ((p.tq + (p.tr ? 1u : 0u)) * p.upt + kW - 1) / kW;
+    static const int smem_cap = env_int("FP4_B200_GEMV_SMEM_KB", (int)(kMaxSmem / 1024)) * 1024;
+    uint32_t ring = (uint32_t)(((size_t)smem_cap - fixed) / ((size_t)kW * kSlot));
+    if (ring > units_per_warp) ring = units_per_warp;
+    if (ring > (uint32_t)max_ring) ring = (uint32_t)max_ring;
+    if (ring > kMaxRing) ring = kMaxRing;
+    if (ring < 1) ring = 1;
+    p.ring = ring;
+    p.tl = nullptr;
+#ifdef FP4_STREAM_TIMELINE
+    if (g_stream_tl) p.tl = g_stream_tl + (size_t)(g_stream_tl_launch++) * (kNumSMs * kW * 8);
+#endif
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes(batch, K, sizeof(T) == 4 ? 4 : 2);
+    cfg.dynamicSmemBytes = fixed + (size_t)kW * ring * kSlot;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -467,6 +504,10 @@ static int launch_nct(const void* x, const uint8_t* packed, const float* absmax,
 
 }  // namespace
 
+#ifdef FP4_STREAM_TIMELINE
+extern "C" void fp4_b200_debug_stream_timeline(long long* buf) { g_stream_tl = buf; g_stream_tl_launch = 0; }
+#endif
+
 bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested, const void* packed,
                            const void* absmax) {
     static const int disabled = env_int("FP4_B200_GEMV_NO_STREAM", 0);
@@ -479,7 +520,7 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
     if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(absmax) % 16) return false;
     const int nt = nterms(dtype);
     if ((batch * nt * 2 + 7) / 8 > 4) return false;
-    return smem_bytes(batch, K, nt) <= kMaxSmem;
+    return fixed_smem_bytes(batch, K, nt) + (size_t)kW * kSlot <= kMaxSmem;
 }
 
 int gemv_stream_dispatch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
