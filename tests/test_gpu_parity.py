@@ -214,6 +214,53 @@ def test_gemv_rejects_bad_arguments(cuda):
         ext.gemv_fp4(torch.zeros(1, 64, device=cuda), A, am, code, 64, 99, [64, 64])
 
 
+# ---------------------------------------------------------------- dequant-fused tcgen05 GEMM
+def _gemm_case(cuda, dtype, rows, N, K, bs=64, seed=0, bias=False):
+    packed, absmax, _ = synth_quant(N * K, bs, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(rows, K, generator=g).to(dtype)
+    b = (torch.randn(N, generator=g) * 0.1).to(dtype) if bias else None
+    A, am = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda)
+    y = ext.gemm_fp4(x.to(cuda), A, am, None, N, K, bs, None if b is None else b.to(cuda))
+    # what the reference computes: dequantise (bit-exact kernel, checked above) then a GEMM; done in fp32
+    w = ext.dequantize_fp4(A, am, bs, N, K, ST[dtype]).float()
+    ref = x.to(cuda).float() @ w.t()
+    if b is not None:
+        ref = ref + b.to(cuda).float()
+    return y, ref
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,N,K", [(9, 128, 64), (16, 256, 256), (33, 384, 512), (64, 1024, 1024), (100, 200, 320),
+                                      (128, 4096, 4096), (300, 512, 2048), (1000, 1152, 1024)])
+def test_gemm_tcgen05_vs_dequant_then_matmul(cuda, dtype, rows, N, K):
+    y, ref = _gemm_case(cuda, dtype, rows, N, K, seed=rows + N, bias=(rows % 2 == 0))
+    assert y.shape == (rows, N) and y.dtype == dtype
+    err = (y.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+    assert err <= (4e-3 if dtype == torch.bfloat16 else 6e-4)  # output rounding of T only
+
+
+def test_gemm_tcgen05_blocksize_128_and_repeat_is_deterministic(cuda):
+    y0, ref = _gemm_case(cuda, torch.bfloat16, 77, 256, 1024, bs=128, seed=5)
+    y1, _ = _gemm_case(cuda, torch.bfloat16, 77, 256, 1024, bs=128, seed=5)
+    assert torch.equal(y0, y1)
+    assert (y0.float() - ref).abs().max().item() / ref.abs().max().item() <= 4e-3
+
+
+def test_module_dispatch_uses_gemm_for_prefill(cuda):
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    torch.manual_seed(7)
+    w = (torch.randn(384, 512) * 0.05).to(cuda)
+    b = (torch.randn(384) * 0.1).to(cuda)
+    m = torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w, b))
+    x = torch.randn(2, 40, 512, device=cuda, dtype=torch.bfloat16)
+    y = m(x)  # 80 rows: the tcgen05 GEMM
+    assert y.shape == (2, 40, 384) and y.dtype == torch.bfloat16
+    ref = torch.nn.functional.linear(x.float(), m.quant_data.dequantize().float(), b.float())
+    assert (y.float() - ref).abs().max().item() / ref.abs().max().item() <= 4e-3
+
+
 # ---------------------------------------------------------------- against the reference extension itself
 def _ref_ext():
     from oracle.build_ref import load_module

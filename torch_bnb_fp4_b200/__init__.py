@@ -35,7 +35,7 @@ from .ext import ScalarType as ScalarType_
 T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
-GEMM_MIN_ROWS = 64      # rows of x from which the dequant-fused tcgen05 GEMM is used (when built)
+GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
 
 
 class ScalarType(Enum):
@@ -219,7 +219,7 @@ class QuantData:
             if not A.is_contiguous():
                 A = A.contiguous()
             return self._qgemv(A)
-        if (rows >= GEMM_MIN_ROWS and self.nested is None
+        if (rows >= GEMM_MIN_ROWS and self.nested is None and self._code_is_std
                 and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype)):
             if not A.is_contiguous():
                 A = A.contiguous()

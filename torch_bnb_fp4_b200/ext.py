@@ -292,7 +292,7 @@ def gemm_fp4_supported(rows: int, M: int, N: int, blocksize: int, dtype: torch.d
             and blocksize % 64 == 0 and rows > 0 and GEMM_AVAILABLE)
 
 
-GEMM_AVAILABLE = False  # flipped by the package once the tcgen05 kernel is built in
+GEMM_AVAILABLE = True  # the tcgen05 kernel is part of libfp4_b200.so
 
 
 def _a_in_dtype(A_in: torch.Tensor) -> ScalarType:
