@@ -15,10 +15,13 @@
 // overlaps the main loop of tile i+1.
 //
 // Warp roles of the persistent CTA (one per SM, 320 threads):
-//   warp 0      TMA producer: activation tiles [tokens x 64 k] -> shared memory (128-byte swizzle)
+//   warp 0      TMA producer: activation tiles [tokens x 64 k] -> shared memory (128-byte swizzle), and the
+//               PACKED weight tile [128 rows x 128 B = 4 k blocks] into its own ring (16 KiB boxes keep
+//               ~48 KB of the 0.5 B/weight stream in flight per SM; register prefetch cannot)
 //   warp 1      MMA issuer (one lane): tcgen05.mma kind::f16, 4 x (128 x tokens x 16) per stage;
 //               tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5   dequantisers: thread r owns weight row r of the tile; per 64-k block it builds the 8
+//   warps 2-5   dequantisers: thread r owns weight row r of the tile; per 64-k block it reads its 32 packed
+//               bytes from the ring (swizzled: conflict-free), builds the 8
 //               possible magnitudes RN_T(|code_i| * absmax) once, then decodes 64 nibbles with byte
 //               permutes (PRMT as an 8-entry table, sign bit merged with one LOP3) and writes its
 //               128-byte row in the swizzled K-major layout
@@ -40,6 +43,8 @@ constexpr int BW = 128;  // weight rows per tile (MMA M)
 constexpr int BK = 64;   // k per pipeline stage = one 128-byte swizzle row of 16-bit elements
 constexpr int kThreads = 320;
 constexpr uint32_t kStageA = BW * BK * 2;  // 16 KiB of dequantised weights per stage
+constexpr int kWSlots = 3;                 // ring of packed-weight boxes
+constexpr uint32_t kWBox = BW * 128;       // 128 rows x 128 packed bytes = 4 k blocks
 
 // 12 * |code| of the bitsandbytes FP4 table is exact in binary; the table itself (fp32) is the one the
 // dequant kernel multiplies with
@@ -127,16 +132,20 @@ struct Pack2<__half> {
 // BT: tokens per tile (MMA N).  TMEM holds two accumulators of BT columns.
 template <typename T, int BT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Params p, int stages) {
+gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                        const __grid_constant__ Params p, int stages) {
     constexpr uint32_t kStageB = BT * BK * 2;
     constexpr uint32_t kTmemCols = 2 * BT < 32 ? 32 : 2 * BT;  // powers of two for BT in {16,...,256}
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sA = smem_u32(smem);                       // [stages][128 rows][128 B]
     const uint32_t sB = sA + (uint32_t)stages * kStageA;      // [stages][BT rows][128 B]
-    const uint32_t bars = sB + (uint32_t)stages * kStageB;    // full[stages], empty[stages], tfull[2], tempty[2]
+    const uint32_t sW = sB + (uint32_t)stages * kStageB;      // [kWSlots][128 rows][128 B] packed weights
+    const uint32_t bars = sW + kWSlots * kWBox;  // full[stages], empty[stages], tfull[2], tempty[2], wfull[], wempty[]
     const uint32_t full0 = bars, empty0 = bars + stages * 8, tfull0 = bars + stages * 16, tempty0 = tfull0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)stages * (kStageA + kStageB) + stages * 16 + 32);
+    const uint32_t wfull0 = tempty0 + 16, wempty0 = wfull0 + kWSlots * 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)stages * (kStageA + kStageB) + kWSlots * kWBox +
+                                                      stages * 16 + 32 + kWSlots * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -148,9 +157,14 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             mbar_init(tfull0 + a * 8, 1);       // tcgen05.commit after the last k block
             mbar_init(tempty0 + a * 8, 128);    // epilogue threads
         }
+        for (int w = 0; w < kWSlots; ++w) {
+            mbar_init(wfull0 + w * 8, 1);       // TMA producer (with tx bytes)
+            mbar_init(wempty0 + w * 8, 128);    // dequantiser threads
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     }
     if (warp == 1) {  // one warp allocates TMEM and later frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -165,12 +179,19 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const uint32_t nkb = p.nkb;
 
     if (warp == 0) {
-        // ===== TMA producer: activation tiles =====
+        // ===== TMA producer: packed weight boxes (one per 4 k blocks) and activation tiles =====
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, wit = 0;
             for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const uint32_t tt = tile % p.tiles_t;
+                const uint32_t tt = tile % p.tiles_t, wt = tile / p.tiles_t;
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    if ((kb & 3) == 0) {
+                        const uint32_t ws = wit % kWSlots, wph = (wit / kWSlots) & 1;
+                        ++wit;
+                        mbar_wait(wempty0 + ws * 8, wph ^ 1);
+                        mbar_expect_tx(wfull0 + ws * 8, kWBox);
+                        tma_load_2d(sW + ws * kWBox, &tmW, (int)(kb * 32), (int)(wt * BW), wfull0 + ws * 8);
+                    }
                     const uint32_t s = it % stages, ph = (it / stages) & 1;
                     mbar_wait(empty0 + s * 8, ph ^ 1);
                     mbar_expect_tx(full0 + s * 8, kStageB);
@@ -206,81 +227,94 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     } else if (warp < 6) {
         // ===== dequantisers: thread r = weight row r of the tile =====
         const int r = threadIdx.x - 64;
-        const uint32_t rowb = (uint32_t)p.K >> 1;
         const uint32_t srow = (uint32_t)r * 128, sx = (uint32_t)(r & 7);
         float mag[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mag[i] = kBnbMag[i];
-        uint32_t it = 0;
-        constexpr int PD = 4;  // k blocks of packed weights kept in flight in registers
-        uint4 wa[PD], wb[PD];
+        uint32_t it = 0, wit = 0;
+        constexpr int PD = 4;  // k blocks per packed-weight box; absmax values prefetched one box ahead
         float am[PD];
-        // loader state runs PD k blocks ahead of the consumer, across tile boundaries
-        uint32_t ld_tile = blockIdx.x, ld_kb = 0;
-        auto load = [&](uint4& a, uint4& b, float& m) {
+        // absmax loader runs one box (PD k blocks) ahead of the consumer, across tile boundaries
+        uint32_t ld_tile = blockIdx.x, ld_kb0 = 0;
+        auto load_box_absmax = [&]() {
             if (ld_tile < p.num_tiles) {
                 const uint32_t wt = ld_tile / p.tiles_t;
                 uint32_t row = wt * BW + (uint32_t)r;
                 row = row < (uint32_t)p.N ? row : (uint32_t)p.N - 1;
-                const uint8_t* src = p.packed + (size_t)row * rowb + ld_kb * 32;
-                a = ldg_stream_u4(src);
-                b = ldg_stream_u4(src + 16);
-                m = __ldg(p.absmax + (((size_t)row * nkb + ld_kb) >> p.bs_shift));
-                if (++ld_kb == nkb) {
-                    ld_kb = 0;
+                const size_t b0 = (size_t)row * nkb + ld_kb0;
+#pragma unroll
+                for (int i = 0; i < PD; ++i)
+                    if (ld_kb0 + i < nkb) am[i] = __ldg(p.absmax + ((b0 + i) >> p.bs_shift));
+                ld_kb0 += PD;
+                if (ld_kb0 >= nkb) {
+                    ld_kb0 = 0;
                     ld_tile += gridDim.x;
                 }
             }
         };
+        load_box_absmax();
+        for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (uint32_t kb0 = 0; kb0 < nkb; kb0 += PD) {
+                const uint32_t ws = wit % kWSlots, wph = (wit / kWSlots) & 1;
+                ++wit;
+                mbar_wait(wfull0 + ws * 8, wph);  // the packed box of k blocks kb0 .. kb0+3 has landed
+                const uint32_t wsrc = sW + ws * kWBox + srow;
+                float amc[PD];
 #pragma unroll
-        for (int i = 0; i < PD; ++i) load(wa[i], wb[i], am[i]);
-        // flat sequence of (tile, k block) stages of this CTA, PD per trip so the slots index registers
-        const uint32_t my_tiles = p.num_tiles > blockIdx.x ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const uint32_t total = my_tiles * nkb;
-        for (uint32_t base = 0; base < total; base += PD) {
+                for (int i = 0; i < PD; ++i) amc[i] = am[i];
+                load_box_absmax();  // absmax of the next box
 #pragma unroll
-            for (int i = 0; i < PD; ++i) {
-                if (base + i < total) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
-                    ++it;
-                    // the 8 magnitudes this (row, block) can take, rounded exactly like the dequant kernel
-                    const float a_ = am[i];
-                    const uint32_t p01 = Pack2<T>::go(__fmul_rn(mag[0], a_), __fmul_rn(mag[1], a_));
-                    const uint32_t p23 = Pack2<T>::go(__fmul_rn(mag[2], a_), __fmul_rn(mag[3], a_));
-                    const uint32_t p45 = Pack2<T>::go(__fmul_rn(mag[4], a_), __fmul_rn(mag[5], a_));
-                    const uint32_t p67 = Pack2<T>::go(__fmul_rn(mag[6], a_), __fmul_rn(mag[7], a_));
-                    // byte tables: low bytes / high bytes of magnitudes 0..3 and 4..7
-                    const uint32_t lo_a = prmt(p01, p23, 0x6420u), hi_a = prmt(p01, p23, 0x7531u);
-                    const uint32_t lo_b = prmt(p45, p67, 0x6420u), hi_b = prmt(p45, p67, 0x7531u);
-                    const uint32_t w[8] = {wa[i].x, wa[i].y, wa[i].z, wa[i].w, wb[i].x, wb[i].y, wb[i].z, wb[i].w};
-                    load(wa[i], wb[i], am[i]);  // refill the slot with the block PD ahead
-                    mbar_wait(empty0 + s * 8, ph ^ 1);
-                    const uint32_t dst = sA + s * kStageA + srow;
+                for (int i = 0; i < PD; ++i) {
+                    if (kb0 + i < nkb) {
+                        const uint32_t s = it % stages, ph = (it / stages) & 1;
+                        ++it;
+                        // this row's 32 packed bytes of the k block: 16-byte chunks 2i, 2i+1 of the swizzled row
+                        uint4 qa, qb;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(qa.x), "=r"(qa.y), "=r"(qa.z), "=r"(qa.w)
+                                     : "r"(wsrc + (((uint32_t)(2 * i) ^ sx) << 4)));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(qb.x), "=r"(qb.y), "=r"(qb.z), "=r"(qb.w)
+                                     : "r"(wsrc + (((uint32_t)(2 * i + 1) ^ sx) << 4)));
+                        // the 8 magnitudes this (row, block) can take, rounded exactly like the dequant kernel
+                        const float a_ = amc[i];
+                        const uint32_t p01 = Pack2<T>::go(__fmul_rn(mag[0], a_), __fmul_rn(mag[1], a_));
+                        const uint32_t p23 = Pack2<T>::go(__fmul_rn(mag[2], a_), __fmul_rn(mag[3], a_));
+                        const uint32_t p45 = Pack2<T>::go(__fmul_rn(mag[4], a_), __fmul_rn(mag[5], a_));
+                        const uint32_t p67 = Pack2<T>::go(__fmul_rn(mag[6], a_), __fmul_rn(mag[7], a_));
+                        // byte tables: low bytes / high bytes of magnitudes 0..3 and 4..7
+                        const uint32_t lo_a = prmt(p01, p23, 0x6420u), hi_a = prmt(p01, p23, 0x7531u);
+                        const uint32_t lo_b = prmt(p45, p67, 0x6420u), hi_b = prmt(p45, p67, 0x7531u);
+                        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                        mbar_wait(empty0 + s * 8, ph ^ 1);
+                        const uint32_t dst = sA + s * kStageA + srow;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        // word c = 8 nibbles = elements 8c..8c+7; nibble j of the word is element j ^ 1
-                        const uint32_t ww = w[c];
-                        const uint32_t wm = ww & 0x77777777u, w4 = ww * 16u;
-                        const uint32_t wmh = __umulhi(wm, 65536u);
-                        uint32_t o[4];
+                        for (int c = 0; c < 8; ++c) {
+                            // word c = 8 nibbles = elements 8c..8c+7; nibble j of the word is element j ^ 1
+                            const uint32_t ww = w[c];
+                            const uint32_t wm = ww & 0x77777777u, w4 = ww * 16u;
+                            const uint32_t wmh = __umulhi(wm, 65536u);
+                            uint32_t o[4];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t sel = h ? wmh : wm;
-                            const uint32_t lo4 = prmt(lo_a, lo_b, sel);
-                            // sign-replicate mode: 0xFF where the nibble's sign bit is set
-                            const uint32_t sg = prmt(ww, w4, h ? 0xBFAEu : 0x9D8Cu);
-                            const uint32_t hi4 = prmt(hi_a, hi_b, sel) | (sg & 0x80808080u);
-                            o[2 * h] = prmt(lo4, hi4, 0x4051u);      // elements (0,1) of the group: nibbles (1,0)
-                            o[2 * h + 1] = prmt(lo4, hi4, 0x6273u);  // elements (2,3): nibbles (3,2)
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t sel = h ? wmh : wm;
+                                const uint32_t lo4 = prmt(lo_a, lo_b, sel);
+                                // sign-replicate mode: 0xFF where the nibble's sign bit is set
+                                const uint32_t sg = prmt(ww, w4, h ? 0xBFAEu : 0x9D8Cu);
+                                const uint32_t hi4 = prmt(hi_a, hi_b, sel) | (sg & 0x80808080u);
+                                o[2 * h] = prmt(lo4, hi4, 0x4051u);      // elements (0,1) of the group: nibbles (1,0)
+                                o[2 * h + 1] = prmt(lo4, hi4, 0x6273u);  // elements (2,3): nibbles (3,2)
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)c ^ sx) << 4)),
+                                         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                                         : "memory");
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)c ^ sx) << 4)),
-                                     "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
-                                     : "memory");
+                        // make the generic-proxy stores visible to the tensor core (async proxy), then signal
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(full0 + s * 8);
                     }
-                    // make the generic-proxy stores visible to the tensor core (async proxy), then signal
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(full0 + s * 8);
                 }
+                mbar_arrive(wempty0 + ws * 8);  // this thread has read its row of the box
             }
         }
     } else {
@@ -366,10 +400,21 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FP4_B200_ERR_UNSUPPORTED;
     }
+    CUtensorMap tmW;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)K / 2, (cuuint64_t)N};
+        const cuuint64_t strides[1] = {(cuuint64_t)K / 2};
+        const cuuint32_t box[2] = {128, (cuuint32_t)BW};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(packed), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FP4_B200_ERR_UNSUPPORTED;
+    }
     constexpr uint32_t kStageB = BT * BK * 2;
-    int stages = (int)((200 * 1024) / (kStageA + kStageB));
-    if (stages > 8) stages = 8;
-    const size_t smem = (size_t)stages * (kStageA + kStageB) + stages * 16 + 64 + 1024;
+    int stages = (int)((196 * 1024 - kWSlots * kWBox) / (kStageA + kStageB));
+    if (stages > 6) stages = 6;
+    const size_t smem = (size_t)stages * (kStageA + kStageB) + kWSlots * kWBox + stages * 16 + 32 + kWSlots * 16 + 64 + 1024;
     auto kern = gemm_fp4_tcgen05_kernel<T, BT>;
     static bool configured = false;
     if (!configured) {
@@ -384,7 +429,7 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     p.tiles_t = ((uint32_t)M + BT - 1) / BT;
     p.num_tiles = p.tiles_t * (((uint32_t)N + BW - 1) / BW);
     const uint32_t grid = p.num_tiles < (uint32_t)kNumSMs ? p.num_tiles : (uint32_t)kNumSMs;
-    kern<<<grid, kThreads, smem, st>>>(tmX, p, stages);
+    kern<<<grid, kThreads, smem, st>>>(tmX, tmW, p, stages);
     return (int)cudaGetLastError();
 }
 
