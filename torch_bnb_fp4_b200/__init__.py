@@ -36,6 +36,7 @@ T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
 GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
+GEMM_MAX_ROWS = 384     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
 
 
 class ScalarType(Enum):
@@ -219,7 +220,7 @@ class QuantData:
             if not A.is_contiguous():
                 A = A.contiguous()
             return self._qgemv(A)
-        if (rows >= GEMM_MIN_ROWS and self.nested is None and self._code_is_std
+        if (GEMM_MIN_ROWS <= rows <= GEMM_MAX_ROWS and self.nested is None and self._code_is_std
                 and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype)):
             if not A.is_contiguous():
                 A = A.contiguous()
