@@ -287,7 +287,7 @@ def run_ours(args, rank, world):
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak, "unit": "GB/s",
                      "frac": gbs / world / peak, "peak_kind": peak_kind, "frac_of_nominal_8TBs": gbs / world / 8000.0,
-                     "kernel": "gemv_mma_kernel (fused dequant-GEMV)",
+                     "kernel": "gemv_stream_kernel (fused dequant-GEMV, IMMA u8 x s8)",
                      "avg_launch_us": t_dev / args.steps / launches_per_step * 1e6,
                      "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step / world,
                      "traffic": traffic_from_profile()},
