@@ -125,6 +125,17 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                   void* workspace, size_t workspace_bytes, void* stream);
 size_t fp4_b200_gemv_workspace_bytes(int N);
 
+/* Grouped fused dequant + GEMV: nmat (1..4) weight matrices with the same K applied to the SAME x in one
+ * launch - out[m][b, r] = T( sum_k x[b,k] * W_m[r,k] + bias_m[r] ) - e.g. the q/k/v or gate/up projections
+ * of a decoder layer, which the reference issues as separate gemv_fp4 calls
+ * (torch_bnb_fp4/__init__.py:471-492 once per nn.Linear).  The arrays are HOST arrays of device pointers /
+ * sizes.  bias may be NULL, or hold NULL entries.  Results equal nmat fp4_b200_gemv calls up to fp32 summation order (deterministic).
+ * Requires FP4_B200_FLAG_CODE_IS_BNB_FP4, blocksize 64, K % 512 == 0, every N[m] % 16 == 0; otherwise
+ * FP4_B200_ERR_UNSUPPORTED (the caller then issues the calls one by one). */
+int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                          const void* const* bias, void* const* out, const int* N, int batch, int K,
+                          int blocksize, int dtype, unsigned flags, void* stream);
+
 /* Dequant-fused tensor-core GEMM for prefill:  out[m, r] = T( sum_k x[m,k] * W[r,k] + bias[r] ),
  * W dequantised tile by tile in shared memory (never written to HBM) and multiplied with tcgen05.mma,
  * fp32 accumulators in TMEM.  Replaces the reference's dequant + cuBLAS pair

@@ -168,6 +168,45 @@ def test_gemv_stream_kernel_is_deterministic_and_matches_stream_k(cuda):
     assert normwise(y0.float().cpu().numpy(), y2.float().cpu().numpy().astype(np.float64)) <= 4e-3
 
 
+def test_gemv_grouped_matches_separate_calls(cuda):
+    """q/k/v-style group (unequal out_features, one with bias) in one launch == three gemv_fp4 calls (the
+    split of a row tile between warps, hence the fp32 summation order, may differ: compare to 1 ulp of T)."""
+    K = 1024
+    Ns = [1024, 256, 2368]
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, K, generator=g).to(dtype).to(cuda)
+    Bs, ams, shapes, biases, singles = [], [], [], [], []
+    for i, N in enumerate(Ns):
+        packed, absmax, _ = synth_quant(N * K, 64, seed=50 + i)
+        A, am = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda)
+        b = (torch.randn(N, generator=g) * 0.1).to(dtype).to(cuda) if i == 1 else None
+        Bs.append(A); ams.append(am); shapes.append([N, K]); biases.append(b)
+        singles.append(ext.gemv_fp4_bias(x, A, am, _code(cuda), 64, ST[dtype], [N, K], b, None, 0))
+    outs = ext.gemv_fp4_grouped(x, Bs, ams, 64, ST[dtype], shapes, biases)
+    assert outs is not None and len(outs) == 3
+    for o, s_, N in zip(outs, singles, Ns):
+        assert o.shape == (2, N)
+        assert (o.float() - s_.float()).abs().max().item() <= 2.0 ** -7 * s_.float().abs().max().item()
+
+
+def test_linear_group_module(cuda):
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    torch.manual_seed(3)
+    mods = [torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear((torch.randn(n, 512) * 0.05).to(cuda)))
+            for n in (1536, 1536)]
+    grp = torch_bnb_fp4.TorchFP4LinearGroup(mods)
+    x = torch.randn(1, 1, 512, device=cuda, dtype=torch.float16)
+    a, b = grp(x)
+    for got, m in ((a, mods[0]), (b, mods[1])):
+        ref = m(x).float()
+        assert (got.float() - ref).abs().max().item() <= 2.0 ** -9 * ref.abs().max().item()
+    xl = torch.randn(3, 20, 512, device=cuda, dtype=torch.float16)  # prefill-sized: per-layer fallback
+    a, b = grp(xl)
+    assert a.shape == (3, 20, 1536) and torch.equal(b, mods[1](xl))
+
+
 def test_gemv_custom_code_is_honoured(cuda):
     code = np.random.default_rng(3).uniform(-1, 1, 16).astype(np.float32)
     y, exact, _ = _gemv_case(cuda, torch.float32, 128, 512, 2, seed=4, code=code)

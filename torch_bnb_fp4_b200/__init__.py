@@ -265,6 +265,35 @@ class TorchFP4Linear(nn.Module):
         return cls(linear, use_codebook_dequant=use_codebook_dequant, name=name)
 
 
+class TorchFP4LinearGroup(nn.Module):
+    """Extension: several TorchFP4Linear layers that consume the SAME input - the
+    q/k/v or gate/up projections of a decoder layer - evaluated with one fused dequant-GEMV launch for
+    decode-sized inputs.  forward(x) returns the tuple of outputs, each equal to calling the layer on its own
+    (up to fp32 summation order); anything the grouped kernel does not cover falls back to exactly that."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        qds = [m.quant_data for m in self.layers]
+        self._groupable = (len(qds) <= 4 and all(q.nested is None and q._code_is_std and q.blocksize == 64
+                                                 for q in qds) and len({q.N for q in qds}) == 1)
+
+    def forward(self, x: torch.Tensor):
+        qds = [m.quant_data for m in self.layers]
+        k = x.shape[-1]
+        rows = x.numel() // k if k else 0
+        if self._groupable and 0 < rows <= GEMV_MAX_BATCH and k == qds[0].N:
+            for q in qds:
+                if x.dtype != q.o_type:
+                    q.set_compute_type(x)
+            xc = x if x.is_contiguous() else x.contiguous()
+            outs = _ext.gemv_fp4_grouped(xc, [q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
+                                         [q._Bshape for q in qds], [q._bias_t for q in qds])
+            if outs is not None:
+                return tuple(outs)
+        return tuple(m(x) for m in self.layers)
+
+
 @torch.no_grad()
 def swap_linear_with_bnb_linear(linear: nn.Linear, dtype=torch.float16):
     """nn.Linear -> (unquantised) LinearFP4 carrying the same weights (reference :717-747)."""

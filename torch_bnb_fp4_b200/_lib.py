@@ -18,7 +18,7 @@ FLAG_NO_STREAM = 16
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
     "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
-    "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemm",
+    "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemm",
     "fp4_b200_quantize",
 ]
 
@@ -46,6 +46,8 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_gemv.argtypes = [vp, vp, vp, ctypes.POINTER(Nested), vp, vp, vp, i32, i32, i32,
                                   i32, i32, u32, vp, ctypes.c_size_t, vp]
     lib.fp4_b200_gemv_workspace_bytes.argtypes = [i32]
+    lib.fp4_b200_gemv_grouped.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                          ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32, vp]
     lib.fp4_b200_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp,
                                   ctypes.c_size_t, vp]
     lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]

@@ -27,6 +27,11 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
                            const void* packed, const void* absmax);
 int gemv_stream_dispatch(const void*, const uint8_t*, const float*, const void*, void*, int, int, int, int,
                          cudaStream_t);
+bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int blocksize, int dtype,
+                                 const uint8_t* const* packed, const float* const* absmax);
+int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                               const void* const* bias, void* const* out, const int* N, int batch, int K, int dtype,
+                               cudaStream_t st);
 int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float*, const void*,
                           void*, int, int, int, int, int, unsigned, cudaStream_t);
 }  // namespace fp4b200
@@ -122,6 +127,22 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
     }
     return gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
                                  bs_log2, dtype, (cudaStream_t)stream);
+}
+
+int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                          const void* const* bias, void* const* out, const int* N, int batch, int K,
+                          int blocksize, int dtype, unsigned flags, void* stream) {
+    if (!x || !packed || !absmax || !out || !N) return FP4_B200_ERR_NULL;
+    if (nmat < 1 || nmat > 4) return FP4_B200_ERR_SHAPE;
+    if (batch < 1 || batch > 8) return FP4_B200_ERR_BATCH;
+    if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16 && dtype != FP4_B200_F32) return FP4_B200_ERR_DTYPE;
+    if (!(flags & FP4_B200_FLAG_CODE_IS_BNB_FP4)) return FP4_B200_ERR_UNSUPPORTED;  // bitsandbytes table only
+    for (int m = 0; m < nmat; ++m)
+        if (!packed[m] || !absmax[m] || !out[m]) return FP4_B200_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(x) % 16) return FP4_B200_ERR_ALIGN;
+    if (!gemv_stream_group_supported(nmat, batch, N, K, blocksize, dtype, packed, absmax))
+        return FP4_B200_ERR_UNSUPPORTED;
+    return gemv_stream_group_dispatch(x, nmat, packed, absmax, bias, out, N, batch, K, dtype, (cudaStream_t)stream);
 }
 
 size_t fp4_b200_gemv_workspace_bytes(int N) { return N > 0 ? gemv_imma_workspace_bytes(N) : 0; }

@@ -66,13 +66,19 @@ constexpr uint32_t kMaxSmem = 226 * 1024; // per CTA: half an SM, so the next la
 constexpr uint32_t kSlot = 4096 + 512;    // one unit: 4 steps x 2 row halves x 32 lanes x 16 B, then 32 lanes x 16 B of absmax
 constexpr uint32_t kMaxRing = 4;
 
+constexpr int kMaxGroup = 4;  // weight matrices sharing one x in a grouped launch (q/k/v, gate/up)
+
 struct Params {
     const void* x;
-    const uint8_t* packed;
-    const float* absmax;
-    const void* bias;
-    void* out;
-    int batch, N, K;
+    // per matrix, rebased so that they index by GLOBAL row (rows of the matrices concatenated):
+    // vpacked[m] + grow * K/2, vabsmax[m] + grow * K/64, vout[m][b * Nm[m] + grow], vbias[m][grow]
+    const uint8_t* vpacked[kMaxGroup];
+    const float* vabsmax[kMaxGroup];
+    const void* vbias[kMaxGroup];  // may be NULL
+    void* vout[kMaxGroup];
+    int Nm[kMaxGroup];             // out_features of matrix m (row pitch of its output)
+    uint32_t tstart[kMaxGroup];    // first global tile of matrix m (tstart[0] = 0; unused entries = UINT32_MAX)
+    int batch, K;
     uint32_t upt;     // units per row tile = K / 512
     uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
     uint32_t ring;    // unit slots per warp (1..kMaxRing)
@@ -164,12 +170,22 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     uint32_t tl_a, ku_a;  // CTA-local tile and unit-in-tile of the first unit
     p.by_upt.divmod(ua, tl_a, ku_a);
 
+    // matrix of a global tile (grouped launches: the matrices' row tiles are numbered consecutively)
+    auto mat_of = [&](uint32_t gt) {
+        return (int)(gt >= p.tstart[1]) + (int)(gt >= p.tstart[2]) + (int)(gt >= p.tstart[3]);
+    };
     // loader: lane (g, t) reads 16 B of row g and 16 B of row g + 8 per 128-k step; 4 steps per unit
-    const size_t trow = (size_t)(tile0 + tl_a) * 16;
-    const uint8_t* wp = p.packed + (trow + g) * rowb + ku_a * 256 + t * 16;
     const uint32_t row8 = 8 * rowb;
-    // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds 4 of them: row g + 8 (t & 1), blocks 4 (t >> 1) ..
-    const float* ap = p.absmax + (trow + g + 8 * (t & 1)) * nkb + ku_a * 8 + 4 * (t >> 1);
+    const uint8_t* wp;
+    const float* ap;  // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds row g + 8 (t & 1), blocks 4 (t >> 1) ..
+    uint32_t ld_gt = tile0 + tl_a;
+    auto loader_at = [&](uint32_t gt, uint32_t kunit) {
+        const int m = mat_of(gt);
+        const size_t trow = (size_t)gt * 16;
+        wp = p.vpacked[m] + (trow + g) * rowb + kunit * 256 + t * 16;
+        ap = p.vabsmax[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
+    };
+    loader_at(ld_gt, ku_a);
     TL_STAMP(0);
     uint32_t ld_ku = ku_a, issued = 0;
     // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
@@ -182,8 +198,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         cp_async_ca16(dst + 4096, ap);
         if (++ld_ku == p.upt) {
             ld_ku = 0;
-            wp += 256 + 15 * (size_t)rowb;
-            ap += 8 + 15 * (size_t)nkb;
+            loader_at(++ld_gt, 0);  // next row tile (possibly the next matrix of the group)
         } else {
             wp += 256;
             ap += 8;
@@ -272,14 +287,16 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 #pragma unroll
     for (int ct = 0; ct < NCT; ++ct) acc[ct][0] = acc[ct][1] = 0.f;
 
-    const T* bias = reinterpret_cast<const T*>(p.bias);
-    T* out = reinterpret_cast<T*>(p.out);
     float* myPart = sPart + (size_t)warp * 2 * batch * 16;
 
     // finish this warp's share (cnt units) of CTA-local tile tl
     auto flush = [&](uint32_t tl, uint32_t cnt) {
         const uint32_t row0 = (tile0 + tl) * 16;
         const bool whole = cnt == p.upt;
+        const int mm = mat_of(tile0 + tl);
+        const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
+        T* out = reinterpret_cast<T*>(p.vout[mm]);
+        const size_t Nm = (size_t)p.Nm[mm];
         float* part = myPart + (tl == tl_a ? 0 : batch * 16);
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
@@ -311,8 +328,8 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                         v0 += DT<T>::to_f32(bias[r0]);
                         v1 += DT<T>::to_f32(bias[r1]);
                     }
-                    out[(size_t)b * p.N + r0] = DT<T>::from_f32(v0);
-                    out[(size_t)b * p.N + r1] = DT<T>::from_f32(v1);
+                    out[(size_t)b * Nm + r0] = DT<T>::from_f32(v0);
+                    out[(size_t)b * Nm + r1] = DT<T>::from_f32(v1);
                 } else {
                     part[b * 16 + g] = v0;
                     part[b * 16 + g + 8] = v1;
@@ -425,8 +442,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 v += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e];
             }
             const uint32_t row = (tile0 + tt) * 16 + (e & 15), b = e >> 4;
+            const int mm = mat_of(tile0 + tt);
+            const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
-            out[(size_t)b * p.N + row] = DT<T>::from_f32(v);
+            reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
         }
     }
     TL_STAMP(7);
@@ -443,9 +462,17 @@ static size_t fixed_smem_bytes(int batch, int K, int nt) {
     return (size_t)batch * nt * K + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
 }
 
+struct Group {
+    int nmat;
+    const uint8_t* packed[kMaxGroup];
+    const float* absmax[kMaxGroup];
+    const void* bias[kMaxGroup];
+    void* out[kMaxGroup];
+    int N[kMaxGroup];
+};
+
 template <typename T, int NCT>
-static int launch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
-                  int batch, int N, int K, cudaStream_t st) {
+static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
     auto kern = gemv_stream_kernel<T, NCT>;
     static bool configured = false;
     if (!configured) {
@@ -455,11 +482,27 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     }
     static const int use_pdl = env_int("FP4_B200_GEMV_PDL", 1);
     static const int max_ring = env_int("FP4_B200_GEMV_RING", (int)kMaxRing);
-    const uint32_t tiles = (uint32_t)N / 16;
-    const uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     Params p;
-    p.x = x; p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;
-    p.batch = batch; p.N = N; p.K = K;
+    p.x = x;
+    p.batch = batch; p.K = K;
+    uint32_t tiles = 0;
+    for (int m = 0; m < kMaxGroup; ++m) {
+        if (m < gr.nmat) {
+            // rebase to global rows (integer arithmetic on addresses; never dereferenced outside the matrix)
+            const size_t grow0 = (size_t)tiles * 16;
+            p.tstart[m] = tiles;
+            p.vpacked[m] = gr.packed[m] - grow0 * ((size_t)K / 2);
+            p.vabsmax[m] = gr.absmax[m] - grow0 * ((size_t)K / 64);
+            p.vbias[m] = gr.bias[m] ? reinterpret_cast<const uint8_t*>(gr.bias[m]) - grow0 * sizeof(T) : nullptr;
+            p.vout[m] = reinterpret_cast<uint8_t*>(gr.out[m]) - grow0 * sizeof(T);
+            p.Nm[m] = gr.N[m];
+            tiles += (uint32_t)gr.N[m] / 16;
+        } else {
+            p.tstart[m] = 0xffffffffu;
+            p.vpacked[m] = nullptr; p.vabsmax[m] = nullptr; p.vbias[m] = nullptr; p.vout[m] = nullptr; p.Nm[m] = 0;
+        }
+    }
+    const uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     p.upt = (uint32_t)K / 512;
     p.tq = tiles / grid; p.tr = tiles % grid;
     p.by_upt = FastDiv(p.upt);
@@ -492,14 +535,20 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
 }
 
 template <typename T, int NT>
-static int launch_nct(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
-                      int batch, int N, int K, cudaStream_t st) {
+static int launch_nct(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
     const int nct = (batch * NT * 2 + 7) / 8;
-#define FP4_GO(NCT) launch<T, NCT>(x, packed, absmax, bias, out, batch, N, K, st)
-    if (nct <= 1) return FP4_GO(1);
-    if (nct <= 2) return FP4_GO(2);
-    return FP4_GO(4);
-#undef FP4_GO
+    if (nct <= 1) return launch<T, 1>(x, gr, batch, K, st);
+    if (nct <= 2) return launch<T, 2>(x, gr, batch, K, st);
+    return launch<T, 4>(x, gr, batch, K, st);
+}
+
+static int dispatch_group(const void* x, const Group& gr, int batch, int K, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case FP4_B200_F16: return launch_nct<__half, 2>(x, gr, batch, K, st);
+        case FP4_B200_BF16: return launch_nct<__nv_bfloat16, 2>(x, gr, batch, K, st);
+        case FP4_B200_F32: return launch_nct<float, 4>(x, gr, batch, K, st);
+        default: return FP4_B200_ERR_DTYPE;
+    }
 }
 
 }  // namespace
@@ -525,16 +574,38 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
 
 int gemv_stream_dispatch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
                          int batch, int N, int K, int dtype, cudaStream_t st) {
-    switch (dtype) {
-        case FP4_B200_F16:
-            return launch_nct<__half, 2>(x, packed, absmax, bias, out, batch, N, K, st);
-        case FP4_B200_BF16:
-            return launch_nct<__nv_bfloat16, 2>(x, packed, absmax, bias, out, batch, N, K, st);
-        case FP4_B200_F32:
-            return launch_nct<float, 4>(x, packed, absmax, bias, out, batch, N, K, st);
-        default:
-            return FP4_B200_ERR_DTYPE;
+    Group gr = {};
+    gr.nmat = 1;
+    gr.packed[0] = packed; gr.absmax[0] = absmax; gr.bias[0] = bias; gr.out[0] = out; gr.N[0] = N;
+    return dispatch_group(x, gr, batch, K, dtype, st);
+}
+
+// Several weight matrices with the same K applied to the same x in ONE launch (q/k/v, gate/up): their row
+// tiles are numbered consecutively and dealt to the CTAs as if they were one matrix.
+bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int blocksize, int dtype,
+                                 const uint8_t* const* packed, const float* const* absmax) {
+    if (nmat < 1 || nmat > kMaxGroup) return false;
+    long total = 0;
+    for (int m = 0; m < nmat; ++m) {
+        if (N[m] <= 0 || N[m] % 16 != 0) return false;
+        if (reinterpret_cast<uintptr_t>(packed[m]) % 16 || reinterpret_cast<uintptr_t>(absmax[m]) % 16) return false;
+        total += N[m];
     }
+    if (total > (1 << 24)) return false;
+    // same rules as one matrix of `total` rows
+    return gemv_stream_supported(batch, (int)total, K, blocksize, dtype, false, packed[0], absmax[0]);
+}
+
+int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                               const void* const* bias, void* const* out, const int* N, int batch, int K, int dtype,
+                               cudaStream_t st) {
+    Group gr = {};
+    gr.nmat = nmat;
+    for (int m = 0; m < nmat; ++m) {
+        gr.packed[m] = packed[m]; gr.absmax[m] = absmax[m]; gr.bias[m] = bias ? bias[m] : nullptr;
+        gr.out[m] = out[m]; gr.N[m] = N[m];
+    }
+    return dispatch_group(x, gr, batch, K, dtype, st);
 }
 
 }  // namespace fp4b200

@@ -258,6 +258,49 @@ def gemv_fp4_bias(A, B, absmax, datatype, blocksize, dtype, Bshape, bias=None, n
                  "gemv_fp4_bias")
 
 
+def gemv_fp4_grouped(A: torch.Tensor, Bs: Sequence[torch.Tensor], absmaxes: Sequence[torch.Tensor],
+                     blocksize: int, dtype, Bshapes: Sequence[Sequence[int]],
+                     biases: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    """Extension: ONE launch for several bitsandbytes-FP4 weights that share the input (q/k/v, gate/up).
+    Returns a list of outputs equal (up to fp32 summation order) to calling gemv_fp4_bias per weight, or None when the shapes are
+    outside the grouped kernel's domain (the caller then issues the calls one by one)."""
+    _check_in(A, "A")
+    dt = get_scalar_type(dtype)
+    if A.dtype != dt:
+        raise RuntimeError(f"A is {A.dtype} but dtype argument says {dt}")
+    n = len(Bs)
+    if n < 1 or n > 4 or len(absmaxes) != n or len(Bshapes) != n:
+        return None
+    k = int(Bshapes[0][1])
+    if any(int(sh[1]) != k for sh in Bshapes) or A.shape[-1] != k:
+        raise RuntimeError("grouped GEMV: every weight must have in_features == A.shape[-1]")
+    batch = A.numel() // k if k else 0
+    if batch < 1 or batch > 8:
+        return None
+    for B, am in zip(Bs, absmaxes):
+        _check_in(B, "B", torch.uint8)
+        _check_in(am, "absmax", torch.float32)
+    outs = [torch.empty(A.shape[:-1] + (int(sh[0]),), dtype=dt, device=A.device) for sh in Bshapes]
+    vp = ctypes.c_void_p
+    pk = (vp * n)(*[B.data_ptr() for B in Bs])
+    am = (vp * n)(*[a.data_ptr() for a in absmaxes])
+    ou = (vp * n)(*[o.data_ptr() for o in outs])
+    ns = (ctypes.c_int * n)(*[int(sh[0]) for sh in Bshapes])
+    bi = None
+    if biases is not None and any(b is not None for b in biases):
+        for b in biases:
+            if b is not None:
+                _check_in(b, "bias", dt)
+        bi = (vp * n)(*[None if b is None else b.data_ptr() for b in biases])
+    with _on_device(A) as st:
+        status = lib.fp4_b200_gemv_grouped(A.data_ptr(), n, pk, am, bi, ou, ns, batch, k, blocksize,
+                                           _CODE_OF[dt], _lib.FLAG_CODE_IS_BNB_FP4, st)
+    if status == -7:  # FP4_B200_ERR_UNSUPPORTED
+        return None
+    check(status, "gemv_fp4_grouped")
+    return outs
+
+
 def gemm_fp4(A_in: torch.Tensor, A: torch.Tensor, absmax: torch.Tensor,
              codebook: Optional[torch.Tensor], M: int, N: int, blocksize: int,
              bias: Optional[torch.Tensor] = None) -> torch.Tensor:
