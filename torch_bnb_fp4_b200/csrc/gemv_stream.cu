@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         ++issued;
     };
     // ---- 1. fill the ring: nothing here depends on the previous kernel in the stream ----------------
-    for (uint32_t r = 0; r < p.ring; ++r) {
-        if (issued < n) issue_unit(ring_a + r * kSlot);
-        cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
-    }
+    // (only the first slot here: issuing a deep ring costs microseconds of LSU time that would delay the
+    // x staging everything else waits for; the other slots are filled right after it)
+    if (issued < n) issue_unit(ring_a);
+    cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
     TL_STAMP(1);
     // x and `out` may be products of the previous kernel: wait for it, then let the next kernel start
     // its own prologue (its prefetches run while this kernel computes)
@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 }
             }
         }
+    }
+    for (uint32_t r = 1; r < p.ring; ++r) {  // the rest of the ring
+        if (issued < n) issue_unit(ring_a + r * kSlot);
+        cp_async_commit();
     }
     __syncthreads();
     TL_STAMP(3);
