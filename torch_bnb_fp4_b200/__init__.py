@@ -231,7 +231,11 @@ class QuantData:
 class TorchFP4Linear(nn.Module):
     """Wrapper for a quantised bitsandbytes LinearFP4 / Linear4bit (reference :621-714)."""
 
-    def __init__(self, lin, use_codebook_dequant: bool = True, name: str = ""):
+    def __init__(self, lin, use_codebook_dequant: bool = True, name: str = "",
+                 materialize_nested_absmax: bool = True):
+        # materialize_nested_absmax (extension): a double-quantised absmax is decoded ONCE at load into
+        # fp32 (bit-exact, SURVEY N5) so decode takes the streaming GEMV; False keeps it nested and decodes
+        # it inside the kernels (0.52 instead of 0.56 bytes per weight, slower kernels)
         super().__init__()
         self.lin = [lin]
         self.in_features = lin.in_features
@@ -249,7 +253,8 @@ class TorchFP4Linear(nn.Module):
         if qtype != "fp4":
             raise ValueError(f"only quant_type='fp4' is supported, got {qtype!r}")
         self.quant_data = QuantData(w.data, w.quant_state, w.quant_state.shape, bias=lin.bias,
-                                    original_lin=lin, use_codebook_dequant=use_codebook_dequant)
+                                    original_lin=lin, use_codebook_dequant=use_codebook_dequant,
+                                    materialize_nested_absmax=materialize_nested_absmax)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.quant_data.forward(x)

@@ -506,14 +506,16 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
             p.vpacked[m] = nullptr; p.vabsmax[m] = nullptr; p.vbias[m] = nullptr; p.vout[m] = nullptr; p.Nm[m] = 0;
         }
     }
-    const uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
+    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", FP4_STREAM_MINB);
+    const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
+    const uint32_t grid = tiles < max_grid ? tiles : max_grid;
     p.upt = (uint32_t)K / 512;
     p.tq = tiles / grid; p.tr = tiles % grid;
     p.by_upt = FastDiv(p.upt);
     // ring depth: no deeper than a warp has units, no larger than shared memory allows
     const size_t fixed = fixed_smem_bytes(batch, K, sizeof(T) == 4 ? 4 : 2);
     const uint32_t units_per_warp = ((p.tq + (p.tr ? 1u : 0u)) * p.upt + kW - 1) / kW;
-    static const int smem_cap = env_int("FP4_B200_GEMV_SMEM_KB", (int)(kMaxSmem / 1024)) * 1024;
+    static const int smem_cap = env_int("FP4_B200_GEMV_SMEM_KB", (int)(kMaxSmem / 1024 / FP4_STREAM_MINB)) * 1024;
     uint32_t ring = (uint32_t)(((size_t)smem_cap - fixed) / ((size_t)kW * kSlot));
     if (ring > units_per_warp) ring = units_per_warp;
     if (ring > (uint32_t)max_ring) ring = (uint32_t)max_ring;
