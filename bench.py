@@ -42,6 +42,18 @@ MISTRAL = dict(hidden=4096, inter=14336, kv=1024, layers=32)
 BLOCKSIZE = 64
 
 
+_REAL_STDOUT = None
+
+
+def emit(text: str) -> None:
+    """The one JSON line, on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+    else:
+        print(text, flush=True)
+
+
 def measured_peak():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
@@ -178,6 +190,30 @@ def make_step_grouped(layers, tp):
     return step
 
 
+def make_step_peer(layers, exchange):
+    """Tensor parallel without collective launches: row-parallel partial sums stay in peer (symmetric) memory and
+    are summed by the next column-parallel launch while it stages x (grouped q/k/v and gate/up launches).
+    Only the model's final hidden state is all-reduced with NCCL (once per token)."""
+    import torch.distributed as dist
+
+    from torch_bnb_fp4_b200.parallel import fused_tp_group_forward as fwd
+
+    def step(h):
+        x = h
+        last = len(layers) - 1
+        for i, m in enumerate(layers):
+            q, _, _ = fwd([m["q"], m["k"], m["v"]], x, exchange)
+            o = fwd([m["o"]], q, exchange, produce=True)
+            _, up = fwd([m["gate"], m["up"]], o, exchange)
+            if i < last:
+                x = fwd([m["down"]], up, exchange, produce=True)
+            else:
+                x = m["down"](up)
+                dist.all_reduce(x)
+        return x
+    return step
+
+
 def time_events(fn, steps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -235,7 +271,43 @@ def run_ours(args, rank, world):
     launches_per_step = len(layers) * 7
     step = make_step(layers, world)
     h0 = torch.randn(1, cfg["hidden"], device=dev).bfloat16()
+    tp_mode = "none" if world == 1 else "nccl all_reduce after every row-parallel layer"
+    nccl_line = None
+    if world > 1 and args.tp_mode == "peer":
+        # headline for N > 1: the peer-memory exchange; the NCCL variant is timed beside it
+        from torch_bnb_fp4_b200.parallel import PeerExchange
+        runner_n = GraphedCallable(step, [h0], warmup=3)
+        for _ in range(args.warmup):
+            runner_n.graph.replay()
+        dist.barrier(); torch.cuda.synchronize()
+        t_n = time_events(runner_n.graph.replay, args.steps)
+        v = torch.tensor([t_n], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        nccl_line = {"tok_per_s": args.steps / float(v.item()), "ms_per_step": float(v.item()) / args.steps * 1e3}
+        ref_out = runner_n(h0).float().clone()
+        del runner_n
+        try:
+            exchange = PeerExchange(cfg["hidden"], torch.bfloat16, dev)
+            step_p = make_step_peer(layers, exchange)
+            with torch.no_grad():
+                step_p(h0)  # shapes outside the streaming kernel raise here (e.g. K/tp % 512 != 0 at tp 8)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:  # noqa: BLE001
+            print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
+            step = step_p
+            tp_mode = ("row-parallel partial sums exchanged through peer (symmetric) memory and summed in the "
+                       "consumer's x staging; q/k/v and gate/up grouped; one NCCL all_reduce per token for the "
+                       "final hidden state")
+        else:
+            nccl_line = None
     runner = GraphedCallable(step, [h0], warmup=max(3, args.warmup))
+    if nccl_line is not None:
+        got = runner(h0).float()
+        nccl_line["max_rel_diff_peer_vs_nccl"] = float((got - ref_out).abs().max() / ref_out.abs().max())
+        exchange.check()
     host_in = torch.randn(1, cfg["hidden"]).bfloat16().pin_memory()
     host_out = torch.empty(1, cfg["hidden"], dtype=torch.bfloat16).pin_memory()
 
@@ -260,12 +332,15 @@ def run_ours(args, rank, world):
     t_dev = maxrank(t_dev)
 
     # extension measured beside the headline: q/k/v and gate/up as grouped launches (128 launches per step)
-    step_g = make_step_grouped(layers, world)
-    runner_g = GraphedCallable(step_g, [h0], warmup=3)
-    for _ in range(args.warmup):
-        runner_g.graph.replay()
-    barrier()
-    t_grp = maxrank(time_events(runner_g.graph.replay, args.steps))
+    if world == 1:
+        step_g = make_step_grouped(layers, world)
+        runner_g = GraphedCallable(step_g, [h0], warmup=3)
+        for _ in range(args.warmup):
+            runner_g.graph.replay()
+        barrier()
+        t_grp = maxrank(time_events(runner_g.graph.replay, args.steps))
+    else:
+        t_grp = None
 
     # end to end: pinned host input -> H2D -> replay -> D2H of the result, every step
     def e2e_step():
@@ -322,15 +397,19 @@ def run_ours(args, rank, world):
                      "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step / world,
                      "traffic": traffic_from_profile()},
         "clocks": clk.summary(),
-        "grouped_launches": {"value": nbytes * args.steps / t_grp / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_grp,
+        "tp_collective": tp_mode,
+        "grouped_launches": None if t_grp is None else {"value": nbytes * args.steps / t_grp / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_grp,
                              "ms_per_step": t_grp / args.steps * 1e3, "launches_per_step": len(layers) * 4,
                              "frac_of_peak": nbytes * args.steps / t_grp / 1e9 / world / peak,
                              "what": "extension: q/k/v and gate/up each issued as one fp4_b200_gemv_grouped launch "
                                      "(TorchFP4LinearGroup); same arithmetic up to fp32 summation order, 4 instead of 7 launches per layer"},
     }
+    if nccl_line is not None:
+        nccl_line["value"] = nbytes / (nccl_line["ms_per_step"] * 1e-3) / 1e9
+        line["nccl_allreduce_variant"] = nccl_line
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args.cpu_seconds)
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_reference(args, rank, world):
@@ -426,11 +505,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mistral7b", choices=["mistral7b", "c1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp-mode", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer-memory exchange fused into the consumer launch (default) or NCCL all_reduce")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
+    if world > 1:
+        # NCCL / torch print banners on stdout; the contract is ONE JSON line there: park stdout on stderr
+        # until the line is printed
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -443,7 +530,12 @@ def main():
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # symmetric-memory handles keep peer mappings alive; tearing the process group down under them can
+        # block, so leave through _exit once every rank has passed the barrier
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,30 @@ typedef struct {
     int blocksize2;          /* state2.blocksize (256 in bitsandbytes)        */
 } fp4_b200_nested_t;
 
+/* Tensor-parallel exchange through peer (symmetric) memory, for fp4_b200_gemv_grouped_tp (16-bit dtypes).
+ * A row-parallel layer (o / down projection) produces PARTIAL sums.  Instead of a collective launch it PUSHES
+ * them, element by element as 32-bit words {value16, tag16 = epoch}, into the exchange buffer of every rank
+ * (plain NVLink stores, no fences, no flags: each word validates itself, as in NCCL's LL protocol); the
+ * consumer - the next column-parallel layer - reads only its LOCAL buffer while it stages x, re-reading words
+ * whose tag is not yet the current epoch, and sums the ranks' partials in rank order.
+ * Exchange buffer of a rank: [2 slots (epoch parity)][world][slot_bytes / 4 words]; rank r's partial for epoch e
+ * lives at word offset ((e & 1) * world + r) * slot_bytes / 4 + (b * N + row).  Must start zero-filled.
+ *   consumer:  in_world > 1, in_base = this rank's exchange buffer;
+ *   producer:  out_world > 1, out_peer_base[q] = rank q's exchange buffer as mapped on this GPU (the call's
+ *              out[0] is ignored), out_rank = this rank.
+ * epochs: two uint32 in local device memory, zero-initialised: [0] = last epoch published by this rank's
+ * producers, [1] = last epoch its consumers finished.  Every rank must issue the same sequence of calls, and a
+ * published partial must be consumed before the next one is published.  err is set to 1 if a wait gave up. */
+typedef struct {
+    int in_world;
+    const void* in_base;
+    uint32_t slot_bytes;
+    int out_world, out_rank;
+    void* out_peer_base[8];
+    uint32_t* epochs;
+    uint32_t* err;
+} fp4_b200_tp_t;
+
 int fp4_b200_abi_version(void);
 const char* fp4_b200_status_string(int status);
 
@@ -151,6 +175,12 @@ int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, con
  * packed: ceil(n/2) bytes, absmax: ceil(n/blocksize) floats. */
 int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
                       float* absmax, void* stream);
+
+/* fp4_b200_gemv_grouped with the tensor-parallel exchange of fp4_b200_tp_t (tp may be NULL = plain).
+ * x may be NULL when tp->in_world > 1 (x is then the sum of the ranks' partials). */
+int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                             const void* const* bias, void* const* out, const int* N, int batch, int K,
+                             int blocksize, int dtype, unsigned flags, const fp4_b200_tp_t* tp, void* stream);
 
 #ifdef __cplusplus
 }

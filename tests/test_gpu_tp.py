@@ -1,0 +1,27 @@
+"""Tensor-parallel exchange through peer memory (torch_bnb_fp4_b200.parallel.PeerExchange): needs >= 2 GPUs of one
+box (skipped otherwise).  Runs tools/tp_fused_check.py under torchrun: the peer-memory step must agree with the
+NCCL step and the unsharded layers, be bit-identical across ranks and replay-stable under CUDA graphs."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_peer_exchange_two_ranks():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "tp_fused_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT).stdout
+    m = re.findall(r"nccl vs full ([0-9.e+-]+)\s+peer vs full ([0-9.e+-]+)\s+peer run-to-run ([0-9.e+-]+)", out)
+    assert len(m) == 2, out
+    for nccl, peer, rr in m:
+        assert float(peer) <= 2e-2 and float(peer) <= 2.0 * float(nccl) + 1e-3 and float(rr) == 0.0
+    assert out.count("ranks agree bit for bit: True") == 2
+    assert len(re.findall(r"graph replay vs eager 0\.00e\+00", out)) == 2

@@ -1,0 +1,57 @@
+"""2-rank check of the peer-memory tensor-parallel exchange against the NCCL path and the unsharded layers.
+torchrun --nproc-per-node 2 tools/tp_fused_check.py"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+dev = torch.device("cuda", torch.cuda.current_device())
+from torch_bnb_fp4_b200.graph import GraphedCallable  # noqa: E402
+from torch_bnb_fp4_b200.parallel import PeerExchange  # noqa: E402
+
+cfg = dict(hidden=2048, inter=4096, kv=1024, layers=3)
+tp_layers, _ = bench.build_stack(cfg, dev, rank, world)
+full_layers, _ = bench.build_stack(cfg, dev, 0, 1)
+h0 = torch.randn(1, cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(5)).bfloat16()
+def say(msg):
+    torch.cuda.synchronize()
+    print(f"[rank {rank}] {msg}", flush=True)
+
+
+with torch.no_grad():
+    say("stacks built")
+    ref_full = bench.make_step(full_layers, 1)(h0).float()
+    say("full done")
+    ref_nccl = bench.make_step(tp_layers, world)(h0).float()
+    say("nccl done")
+    ex = PeerExchange(cfg["hidden"], torch.bfloat16, dev)
+    say("exchange ready")
+    step_p = bench.make_step_peer(tp_layers, ex)
+    outs = []
+    for i in range(3):
+        outs.append(step_p(h0).float().clone())
+        say(f"peer step {i} done, state {ex.state.tolist()}")
+    ex.check()
+scale = ref_full.abs().max().item()
+print(f"[rank {rank}] nccl vs full {((ref_nccl - ref_full).abs().max() / scale).item():.2e}  "
+      f"peer vs full {((outs[0] - ref_full).abs().max() / scale).item():.2e}  "
+      f"peer run-to-run {((outs[2] - outs[0]).abs().max() / scale).item():.2e}", flush=True)
+allout = [torch.empty_like(outs[0]) for _ in range(world)]
+dist.all_gather(allout, outs[0])
+print(f"[rank {rank}] ranks agree bit for bit: {all(torch.equal(allout[0], o) for o in allout)}", flush=True)
+g = GraphedCallable(step_p, [h0], warmup=3)
+for _ in range(5):
+    og = g(h0).float()
+ex.check()
+print(f"[rank {rank}] graph replay vs eager {((og - outs[0]).abs().max() / scale).item():.2e}", flush=True)
+dist.barrier()
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0)

@@ -18,7 +18,7 @@ FLAG_NO_STREAM = 16
 EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
     "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
-    "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemm",
+    "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
     "fp4_b200_quantize",
 ]
 
@@ -28,6 +28,13 @@ class Nested(ctypes.Structure):
     _fields_ = [("qabsmax", ctypes.c_void_p), ("code2", ctypes.c_void_p),
                 ("absmax2", ctypes.c_void_p), ("offset", ctypes.c_float),
                 ("blocksize2", ctypes.c_int)]
+
+
+class TpExchange(ctypes.Structure):
+    """fp4_b200_tp_t"""
+    _fields_ = [("in_world", ctypes.c_int), ("in_base", ctypes.c_void_p), ("slot_bytes", ctypes.c_uint32),
+                ("out_world", ctypes.c_int), ("out_rank", ctypes.c_int), ("out_peer_base", ctypes.c_void_p * 8),
+                ("epochs", ctypes.c_void_p), ("err", ctypes.c_void_p)]
 
 
 def _load() -> ctypes.CDLL:
@@ -48,6 +55,9 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_gemv_workspace_bytes.argtypes = [i32]
     lib.fp4_b200_gemv_grouped.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                           ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32, vp]
+    lib.fp4_b200_gemv_grouped_tp.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                             ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32,
+                                             ctypes.POINTER(TpExchange), vp]
     lib.fp4_b200_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp,
                                   ctypes.c_size_t, vp]
     lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]

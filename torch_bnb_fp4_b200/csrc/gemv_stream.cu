@@ -83,6 +83,7 @@ struct Params {
     uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
     uint32_t ring;    // unit slots per warp (1..kMaxRing)
     FastDiv by_upt;
+    fp4_b200_tp_t tp;  // tensor-parallel exchange through peer memory (in_world / out_world <= 1: off)
     long long* tl;    // debug timeline (FP4_STREAM_TIMELINE builds): [cta][warp][8] globaltimer ns
 };
 
@@ -140,6 +141,58 @@ __device__ __forceinline__ void cp_async_wait_pending(uint32_t pending) {  // un
         case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
         default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
+// ---- tensor-parallel exchange through peer (symmetric) memory -------------------------------------------
+// A row-parallel layer pushes its partial output, as self-validating 32-bit words {value16, tag16 = epoch},
+// into every rank's exchange buffer over NVLink (no fences, no flags); the consumer sums the ranks' partials
+// out of its LOCAL buffer while it stages x, re-reading words whose tag is not the current epoch yet.
+__device__ __forceinline__ void st_peer_u32(void* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by other GPUs: never the read-only path
+    uint4 r;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ float tp_word_value(uint32_t w) {
+    if constexpr (sizeof(T) == 2 && DT<T>::code == FP4_B200_BF16) {
+        return __uint_as_float(w << 16);
+    } else {
+        return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
+    }
+}
+template <typename T>
+__device__ __forceinline__ uint32_t tp_word(float v, uint32_t tag) {
+    unsigned short h;
+    if constexpr (sizeof(T) == 2 && DT<T>::code == FP4_B200_BF16) {
+        h = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else {
+        h = __half_as_ushort(__float2half_rn(v));
+    }
+    return (uint32_t)h | (tag << 16);
+}
+// 8 consecutive elements of rank `r`'s partial for the epoch with tag `tag`; waits for late words
+template <typename T>
+__device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float (&f)[8], uint32_t* err) {
+    uint32_t spins = 0;
+    for (;;) {
+        const uint4 a = ld_peer_u4(src), b = ld_peer_u4(src + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ok = ok && (w[i] >> 16) == tag;
+        if (ok || ++spins > (1u << 19)) {  // a peer died or the call sequences diverged: flag it, do not hang
+            if (!ok) *err = 1u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = tp_word_value<T>(w[i]);
+            return;
+        }
     }
 }
 
@@ -216,6 +269,22 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
     TL_STAMP(2);
+    // tensor parallel (see the helpers above).  Epochs: [0] = last published by this rank's producers,
+    // [1] = last finished by its consumers; both only change between the kernels that read them.
+    const int in_world = p.tp.in_world, out_world = p.tp.out_world;
+    uint32_t in_tag = 0, out_tag = 0, e_in = 0, e_out = 0;
+    const uint8_t* in_slot = nullptr;
+    size_t out_off = 0;
+    if (in_world > 1) {
+        e_in = __ldcg(p.tp.epochs);
+        in_tag = e_in & 0xFFFFu;
+        in_slot = reinterpret_cast<const uint8_t*>(p.tp.in_base) + (size_t)(e_in & 1u) * in_world * p.tp.slot_bytes;
+    }
+    if (out_world > 1) {
+        e_out = __ldcg(p.tp.epochs + 1) + 1u;
+        out_tag = e_out & 0xFFFFu;
+        out_off = ((size_t)(e_out & 1u) * out_world + p.tp.out_rank) * p.tp.slot_bytes;
+    }
 
     // ---- 2. stage x as s8 residual terms, one power-of-two scale per (batch row, 64-block) ----------
     for (uint32_t i = tid; i < kZeroBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sZero)[i] = 0u;
@@ -225,7 +294,20 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         for (int b = 0; b < batch; ++b) {
             for (int c = tid; c < nchunk; c += kThreads) {
                 float f[8];
-                XLoad<T>::load(x + (size_t)b * K + c * 8, f);
+                if (in_world > 1) {
+                    if constexpr (sizeof(T) == 2) {
+                        const size_t off = ((size_t)b * K + (size_t)c * 8) * 4;
+                        tp_load8<T>(in_slot + off, in_tag, f, p.tp.err);
+                        for (int r = 1; r < in_world; ++r) {  // fixed rank order: every rank computes the same x
+                            float fr[8];
+                            tp_load8<T>(in_slot + (size_t)r * p.tp.slot_bytes + off, in_tag, fr, p.tp.err);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] += fr[i];
+                        }
+                    }
+                } else {
+                    XLoad<T>::load(x + (size_t)b * K + c * 8, f);
+                }
                 float mx = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[i]));
@@ -332,8 +414,19 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                         v0 += DT<T>::to_f32(bias[r0]);
                         v1 += DT<T>::to_f32(bias[r1]);
                     }
-                    out[(size_t)b * Nm + r0] = DT<T>::from_f32(v0);
-                    out[(size_t)b * Nm + r1] = DT<T>::from_f32(v1);
+                    if (out_world > 1) {
+                        if constexpr (sizeof(T) == 2) {
+                            const uint32_t w0 = tp_word<T>(v0, out_tag), w1 = tp_word<T>(v1, out_tag);
+                            for (int q = 0; q < out_world; ++q) {
+                                uint8_t* dst = reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off;
+                                st_peer_u32(dst + ((size_t)b * Nm + r0) * 4, w0);
+                                st_peer_u32(dst + ((size_t)b * Nm + r1) * 4, w1);
+                            }
+                        }
+                    } else {
+                        out[(size_t)b * Nm + r0] = DT<T>::from_f32(v0);
+                        out[(size_t)b * Nm + r1] = DT<T>::from_f32(v1);
+                    }
                 } else {
                     part[b * 16 + g] = v0;
                     part[b * 16 + g + 8] = v1;
@@ -449,8 +542,22 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             const int mm = mat_of(tile0 + tt);
             const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
-            reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
+            if (out_world > 1) {
+                if constexpr (sizeof(T) == 2) {
+                    const uint32_t w_ = tp_word<T>(v, out_tag);
+                    for (int q = 0; q < out_world; ++q)
+                        st_peer_u32(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off +
+                                        ((size_t)b * p.Nm[mm] + row) * 4, w_);
+                }
+            } else {
+                reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
+            }
         }
+    }
+    // epoch bookkeeping for the NEXT kernel of this stream (kernel boundaries order these plain stores)
+    if (blockIdx.x == 0 && tid == 0) {
+        if (out_world > 1) *reinterpret_cast<volatile uint32_t*>(p.tp.epochs) = e_out;
+        if (in_world > 1) *reinterpret_cast<volatile uint32_t*>(p.tp.epochs + 1) = e_in;
     }
     TL_STAMP(7);
 }
@@ -467,6 +574,7 @@ static size_t fixed_smem_bytes(int batch, int K, int nt) {
 }
 
 struct Group {
+    const fp4_b200_tp_t* tp;
     int nmat;
     const uint8_t* packed[kMaxGroup];
     const float* absmax[kMaxGroup];
@@ -489,6 +597,7 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     Params p;
     p.x = x;
     p.batch = batch; p.K = K;
+    if (gr.tp) p.tp = *gr.tp; else { p.tp = fp4_b200_tp_t(); }
     uint32_t tiles = 0;
     for (int m = 0; m < kMaxGroup; ++m) {
         if (m < gr.nmat) {
@@ -604,8 +713,9 @@ bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int b
 
 int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                                const void* const* bias, void* const* out, const int* N, int batch, int K, int dtype,
-                               cudaStream_t st) {
+                               const fp4_b200_tp_t* tp, cudaStream_t st) {
     Group gr = {};
+    gr.tp = tp;
     gr.nmat = nmat;
     for (int m = 0; m < nmat; ++m) {
         gr.packed[m] = packed[m]; gr.absmax[m] = absmax[m]; gr.bias[m] = bias ? bias[m] : nullptr;

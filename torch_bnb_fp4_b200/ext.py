@@ -258,29 +258,46 @@ def gemv_fp4_bias(A, B, absmax, datatype, blocksize, dtype, Bshape, bias=None, n
                  "gemv_fp4_bias")
 
 
-def gemv_fp4_grouped(A: torch.Tensor, Bs: Sequence[torch.Tensor], absmaxes: Sequence[torch.Tensor],
+def gemv_fp4_grouped(A: Optional[torch.Tensor], Bs: Sequence[torch.Tensor], absmaxes: Sequence[torch.Tensor],
                      blocksize: int, dtype, Bshapes: Sequence[Sequence[int]],
-                     biases: Optional[Sequence[Optional[torch.Tensor]]] = None):
+                     biases: Optional[Sequence[Optional[torch.Tensor]]] = None, tp=None,
+                     outs: Optional[Sequence[torch.Tensor]] = None, batch_shape: Optional[Sequence[int]] = None):
     """Extension: ONE launch for several bitsandbytes-FP4 weights that share the input (q/k/v, gate/up).
     Returns a list of outputs equal (up to fp32 summation order) to calling gemv_fp4_bias per weight, or None when the shapes are
-    outside the grouped kernel's domain (the caller then issues the calls one by one)."""
-    _check_in(A, "A")
+    outside the grouped kernel's domain (the caller then issues the calls one by one).
+    `tp` (a _lib.TpExchange, see include/fp4_b200.h) switches on the tensor-parallel exchange through peer
+    memory: with tp.in_world > 1 A may be None (x is the sum of the ranks' partials; give batch_shape),
+    with tp.out_world > 1 `outs` must hold the base of this rank's exchange buffer."""
     dt = get_scalar_type(dtype)
-    if A.dtype != dt:
-        raise RuntimeError(f"A is {A.dtype} but dtype argument says {dt}")
     n = len(Bs)
     if n < 1 or n > 4 or len(absmaxes) != n or len(Bshapes) != n:
         return None
     k = int(Bshapes[0][1])
-    if any(int(sh[1]) != k for sh in Bshapes) or A.shape[-1] != k:
-        raise RuntimeError("grouped GEMV: every weight must have in_features == A.shape[-1]")
-    batch = A.numel() // k if k else 0
+    if A is not None:
+        _check_in(A, "A")
+        if A.dtype != dt:
+            raise RuntimeError(f"A is {A.dtype} but dtype argument says {dt}")
+        if A.shape[-1] != k:
+            raise RuntimeError("grouped GEMV: every weight must have in_features == A.shape[-1]")
+        lead = tuple(A.shape[:-1])
+        batch = A.numel() // k if k else 0
+    else:
+        if tp is None or tp.in_world <= 1 or batch_shape is None:
+            raise RuntimeError("grouped GEMV without an input needs a tensor-parallel exchange and batch_shape")
+        lead = tuple(batch_shape)
+        batch = 1
+        for v in lead:
+            batch *= int(v)
+    if any(int(sh[1]) != k for sh in Bshapes):
+        raise RuntimeError("grouped GEMV: every weight must have the same in_features")
     if batch < 1 or batch > 8:
         return None
     for B, am in zip(Bs, absmaxes):
         _check_in(B, "B", torch.uint8)
         _check_in(am, "absmax", torch.float32)
-    outs = [torch.empty(A.shape[:-1] + (int(sh[0]),), dtype=dt, device=A.device) for sh in Bshapes]
+    dev = Bs[0].device
+    if outs is None:
+        outs = [torch.empty(lead + (int(sh[0]),), dtype=dt, device=dev) for sh in Bshapes]
     vp = ctypes.c_void_p
     pk = (vp * n)(*[B.data_ptr() for B in Bs])
     am = (vp * n)(*[a.data_ptr() for a in absmaxes])
@@ -292,13 +309,14 @@ def gemv_fp4_grouped(A: torch.Tensor, Bs: Sequence[torch.Tensor], absmaxes: Sequ
             if b is not None:
                 _check_in(b, "bias", dt)
         bi = (vp * n)(*[None if b is None else b.data_ptr() for b in biases])
-    with _on_device(A) as st:
-        status = lib.fp4_b200_gemv_grouped(A.data_ptr(), n, pk, am, bi, ou, ns, batch, k, blocksize,
-                                           _CODE_OF[dt], _lib.FLAG_CODE_IS_BNB_FP4, st)
+    with _on_device(Bs[0]) as st:
+        status = lib.fp4_b200_gemv_grouped_tp(None if A is None else A.data_ptr(), n, pk, am, bi, ou, ns, batch, k,
+                                              blocksize, _CODE_OF[dt], _lib.FLAG_CODE_IS_BNB_FP4,
+                                              None if tp is None else ctypes.byref(tp), st)
     if status == -7:  # FP4_B200_ERR_UNSUPPORTED
         return None
     check(status, "gemv_fp4_grouped")
-    return outs
+    return list(outs)
 
 
 def gemm_fp4(A_in: torch.Tensor, A: torch.Tensor, absmax: torch.Tensor,

@@ -131,3 +131,88 @@ class RowParallelFP4Linear(_ShardedFP4Base):
         if self.tp > 1:
             dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
         return y
+
+
+class PeerExchange:
+    """Tensor-parallel exchange through peer (symmetric) memory, shared by all row-parallel layers of a model
+    (include/fp4_b200.h: fp4_b200_tp_t).  A row-parallel layer PUSHES its partial output, as self-validating
+    32-bit words {value16, tag16 = epoch}, into every rank's exchange buffer over NVLink (no fences, no flags,
+    no collective launch); the next column-parallel layer sums the ranks' partials out of its LOCAL buffer
+    while it stages x.  Requires torch symmetric memory (NVLink peers of one box), an initialised process
+    group and a 16-bit activation dtype."""
+
+    def __init__(self, max_features: int, dtype: torch.dtype, device: torch.device, group=None, max_batch: int = 8):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("PeerExchange carries 16-bit activations")
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerExchange supports up to 8 ranks")
+        self.dtype, self.device = dtype, device
+        self.slot_words = ((max_features * max_batch + 63) // 64) * 64       # one rank's region of one slot
+        self.slot_bytes = self.slot_words * 4
+        self.buf = symm_mem.empty(2 * self.world * self.slot_words, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self._hbuf = symm_mem.rendezvous(self.buf, group=group)
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)  # epochs[0], epochs[1], err, pad
+        torch.cuda.synchronize(device)
+        self._hbuf.barrier()
+        self._lib = _lib
+
+    def struct(self, consume: bool, produce: bool):
+        t = self._lib.TpExchange()
+        t.slot_bytes = self.slot_bytes
+        t.epochs = self.state.data_ptr()
+        t.err = self.state.data_ptr() + 8
+        if consume:
+            t.in_world = self.world
+            t.in_base = self.buf.data_ptr()
+        if produce:
+            t.out_world, t.out_rank = self.world, self.rank
+            for q in range(self.world):
+                t.out_peer_base[q] = self._hbuf.buffer_ptrs[q]
+        return t
+
+    def check(self):
+        """Host-side check (synchronises): raises if a kernel gave up waiting for a peer."""
+        if int(self.state[2].item()) != 0:
+            raise RuntimeError("tensor-parallel exchange: a wait for a peer's partial sums timed out")
+
+
+class PeerPartial:
+    """Handle for a row-parallel layer's partial output that lives in the PeerExchange (not a tensor)."""
+
+    def __init__(self, exchange: "PeerExchange", batch_shape, features: int):
+        self.exchange, self.batch_shape, self.features = exchange, tuple(batch_shape), features
+
+
+def fused_tp_group_forward(layers, x, exchange: "PeerExchange", produce: bool = False):
+    """Run TorchFP4Linear `layers` (same in_features) in one grouped launch with the peer-memory exchange:
+    x may be a tensor or a PeerPartial (summed over ranks while staging x); with produce=True (one layer only)
+    the output is published as a PeerPartial instead of being returned as a tensor."""
+    from . import _ext
+
+    qds = [m.quant_data for m in layers]
+    consume = isinstance(x, PeerPartial)
+    tp = exchange.struct(consume, produce)
+    dt = exchange.dtype
+    for q in qds:
+        if q.o_type != dt:
+            q.set_compute_type(torch.empty(0, dtype=dt))
+    lead = x.batch_shape if consume else tuple(x.shape[:-1])
+    outs = None
+    if produce:
+        if len(layers) != 1:
+            raise ValueError("a producer is a single row-parallel layer")
+        outs = [exchange.buf]
+    res = _ext.gemv_fp4_grouped(None if consume else x.contiguous(), [q.A for q in qds], [q.absmax for q in qds], 64,
+                                qds[0].qtype, [q._Bshape for q in qds], [q._bias_t for q in qds], tp=tp, outs=outs,
+                                batch_shape=lead)
+    if res is None:
+        raise RuntimeError("shapes outside the grouped streaming kernel: use the NCCL path")
+    if produce:
+        return PeerPartial(exchange, lead, qds[0].M)
+    return tuple(res)
