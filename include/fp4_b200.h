@@ -176,7 +176,7 @@ int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, con
 int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
                       float* absmax, void* stream);
 
-/* fp4_b200_gemv_grouped with the tensor-parallel exchange of fp4_b200_tp_t (tp may be NULL = plain).
+/* fp4_b200_gemv_grouped with the tensor-parallel exchange described by fp4_b200_tp_t; tp may be NULL (plain).
  * x may be NULL when tp->in_world > 1 (x is then the sum of the ranks' partials). */
 int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                              const void* const* bias, void* const* out, const int* N, int batch, int K,
