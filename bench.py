@@ -193,19 +193,27 @@ def make_step_grouped(layers, tp):
 def make_step_peer(layers, exchange):
     """Tensor parallel without collective launches: row-parallel partial sums stay in peer (symmetric) memory and
     are summed by the next column-parallel launch while it stages x (grouped q/k/v and gate/up launches).
-    Only the model's final hidden state is all-reduced with NCCL (once per token)."""
+    A row-parallel layer whose local K is outside the streaming kernel (K/tp % 256 != 0)
+    keeps the NCCL all_reduce, as does the model's final hidden state."""
     import torch.distributed as dist
 
     from torch_bnb_fp4_b200.parallel import fused_tp_group_forward as fwd
+
+    peer_o = layers[0]["o"].quant_data.N % 256 == 0
+    peer_down = layers[0]["down"].quant_data.N % 256 == 0
 
     def step(h):
         x = h
         last = len(layers) - 1
         for i, m in enumerate(layers):
             q, _, _ = fwd([m["q"], m["k"], m["v"]], x, exchange)
-            o = fwd([m["o"]], q, exchange, produce=True)
+            if peer_o:
+                o = fwd([m["o"]], q, exchange, produce=True)
+            else:
+                o = m["o"](q)
+                dist.all_reduce(o)
             _, up = fwd([m["gate"], m["up"]], o, exchange)
-            if i < last:
+            if peer_down and i < last:
                 x = fwd([m["down"]], up, exchange, produce=True)
             else:
                 x = m["down"](up)

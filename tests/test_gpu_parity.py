@@ -150,7 +150,8 @@ def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
 # 148 CTAs), warps that straddle tiles (upt = 1, 3, 7), every batch size / MMA column-tile count
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N,K,batch", [(2400, 512, 1), (1024, 1536, 2), (2368, 3584, 1), (1600, 1024, 3),
-                                       (1024, 1024, 4), (1024, 512, 5), (1024, 1024, 8), (4736, 512, 2)])
+                                       (1024, 1024, 4), (1024, 512, 5), (1024, 1024, 8), (4736, 512, 2),
+                                       (1024, 1792, 1), (2048, 256, 2), (1536, 768, 3)])
 def test_gemv_stream_kernel_shapes(cuda, dtype, N, K, batch):
     if dtype == torch.float32 and batch > 4:
         batch = 4  # fp32 activations take 4 integer terms: the kernel covers batch <= 4, beyond that stream-K

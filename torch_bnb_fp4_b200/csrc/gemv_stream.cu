@@ -34,7 +34,7 @@
 // share are summed through shared memory in warp order after one __syncthreads (deterministic).
 //
 // Requirements (gemv_stream_supported): bitsandbytes FP4 codebook, blocksize 64, fp32 absmax,
-// K % 512 == 0, N % 16 == 0, enough row tiles to occupy the GPU, x terms fit in shared memory.
+// K % 256 == 0, N % 16 == 0, enough row tiles to occupy the GPU, x terms fit in shared memory.
 #include <cstdlib>
 
 #include "gemv_common.cuh"
@@ -79,7 +79,7 @@ struct Params {
     int Nm[kMaxGroup];             // out_features of matrix m (row pitch of its output)
     uint32_t tstart[kMaxGroup];    // first global tile of matrix m (tstart[0] = 0; unused entries = UINT32_MAX)
     int batch, K;
-    uint32_t upt;     // units per row tile = K / 512
+    uint32_t upt;     // units per row tile = ceil(K / 512)
     uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
     uint32_t ring;    // unit slots per warp (1..kMaxRing)
     FastDiv by_upt;
@@ -196,7 +196,8 @@ __device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float
     }
 }
 
-template <typename T, int NCT>
+// HALF: K % 512 == 256, i.e. the last unit of every row tile holds two steps instead of four
+template <typename T, int NCT, bool HALF>
 __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(const __grid_constant__ Params p) {
     constexpr int TERMS = sizeof(T) == 4 ? 4 : 2;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -243,12 +244,15 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     uint32_t ld_ku = ku_a, issued = 0;
     // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
     auto issue_unit = [&](uint32_t dst) {
+        const uint32_t nst = (HALF && ld_ku + 1 == p.upt) ? 2u : 4u;  // a tile's last unit may be half a unit
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            cp_async_cg16(dst + j * 1024, wp + j * 64);
-            cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
+            if ((uint32_t)j < nst) {
+                cp_async_cg16(dst + j * 1024, wp + j * 64);
+                cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
+            }
         }
-        cp_async_ca16(dst + 4096, ap);
+        if (2 * (t >> 1) < nst) cp_async_ca16(dst + 4096, ap);  // this lane's 4 blocks exist
         if (++ld_ku == p.upt) {
             ld_ku = 0;
             loader_at(++ld_gt, 0);  // next row tile (possibly the next matrix of the group)
@@ -450,8 +454,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             xa[ct] = xbase[ct] + ku * xstep[ct];
             sa[ct] = sbase[ct] + ku * 32;
         }
+        const uint32_t nst_c = (HALF && ku + 1 == p.upt) ? 2u : 4u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            if (HALF && (uint32_t)j >= nst_c) break;
             const uint4 wA4 = lds_u4(sl + j * 1024), wB4 = lds_u4(sl + j * 1024 + 512);
             const uint32_t wA[4] = {wA4.x, wA4.y, wA4.z, wA4.w};
             const uint32_t wB[4] = {wB4.x, wB4.y, wB4.z, wB4.w};
@@ -583,9 +589,9 @@ struct Group {
     int N[kMaxGroup];
 };
 
-template <typename T, int NCT>
+template <typename T, int NCT, bool HALF>
 static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
-    auto kern = gemv_stream_kernel<T, NCT>;
+    auto kern = gemv_stream_kernel<T, NCT, HALF>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -618,7 +624,7 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", FP4_STREAM_MINB);
     const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
     const uint32_t grid = tiles < max_grid ? tiles : max_grid;
-    p.upt = (uint32_t)K / 512;
+    p.upt = ((uint32_t)K + 511) / 512;
     p.tq = tiles / grid; p.tr = tiles % grid;
     p.by_upt = FastDiv(p.upt);
     // ring depth: no deeper than a warp has units, no larger than shared memory allows
@@ -652,9 +658,12 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
 template <typename T, int NT>
 static int launch_nct(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
     const int nct = (batch * NT * 2 + 7) / 8;
-    if (nct <= 1) return launch<T, 1>(x, gr, batch, K, st);
-    if (nct <= 2) return launch<T, 2>(x, gr, batch, K, st);
-    return launch<T, 4>(x, gr, batch, K, st);
+    const bool half = K % 512 != 0;
+#define FP4_GO(NCT) (half ? launch<T, NCT, true>(x, gr, batch, K, st) : launch<T, NCT, false>(x, gr, batch, K, st))
+    if (nct <= 1) return FP4_GO(1);
+    if (nct <= 2) return FP4_GO(2);
+    return FP4_GO(4);
+#undef FP4_GO
 }
 
 static int dispatch_group(const void* x, const Group& gr, int batch, int K, int dtype, cudaStream_t st) {
@@ -678,7 +687,7 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
     static const int min_tiles = env_int("FP4_B200_GEMV_STREAM_MIN_TILES", 48);
     if (disabled || nested || blocksize != 64) return false;
     if (batch < 1 || batch > 8 || N <= 0 || K <= 0) return false;
-    if (K % 512 != 0 || N % 16 != 0) return false;
+    if (K % 256 != 0 || N % 16 != 0) return false;
     if (N / 16 < min_tiles) return false;  // too few row tiles to occupy the GPU: the stream-K kernels split K
     if ((uint64_t)N * (uint64_t)K >= (1ull << 40)) return false;
     if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(absmax) % 16) return false;
