@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 MISTRAL = dict(hidden=4096, inter=14336, kv=1024, layers=32)
+LLAMA70B = dict(hidden=8192, inter=28672, kv=1024, layers=80)  # BASELINE config #4 shapes (38.5 GB of FP4 linears)
 BLOCKSIZE = 64
 
 
@@ -275,6 +276,8 @@ def run_ours(args, rank, world):
     cfg = dict(MISTRAL)
     if args.workload == "c1":
         cfg = dict(hidden=4096, inter=4096, kv=4096, layers=10)  # 70 x 4096x4096 layers = 660 MB > L2
+    elif args.workload == "llama70b":
+        cfg = dict(LLAMA70B)
     layers, nbytes = build_stack(cfg, dev, rank, world)
     launches_per_step = len(layers) * 7
     step = make_step(layers, world)
@@ -381,8 +384,9 @@ def run_ours(args, rank, world):
     peak, peak_kind = measured_peak()
     gbs = nbytes * args.steps / t_dev / 1e9
     line = {
-        "metric": "batch-1 FP4 GEMV HBM GB/s (Mistral-7B-shape decode linear stack)" if args.workload == "mistral7b"
-                  else "batch-1 FP4 GEMV HBM GB/s (4096x4096 layers)",
+        "metric": {"mistral7b": "batch-1 FP4 GEMV HBM GB/s (Mistral-7B-shape decode linear stack)",
+                   "llama70b": "batch-1 FP4 GEMV HBM GB/s (Llama-3-70B-shape decode linear stack)",
+                   "c1": "batch-1 FP4 GEMV HBM GB/s (4096x4096 layers)"}[args.workload],
         "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -511,7 +515,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mistral7b", choices=["mistral7b", "c1"])
+    ap.add_argument("--workload", default="mistral7b", choices=["mistral7b", "c1", "llama70b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tp-mode", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory exchange fused into the consumer launch (default) or NCCL all_reduce")

@@ -280,6 +280,31 @@ def test_gemm_tcgen05_vs_dequant_then_matmul(cuda, dtype, rows, N, K):
     assert err <= (4e-3 if dtype == torch.bfloat16 else 6e-4)  # output rounding of T only
 
 
+def test_gemv_stream_kernel_random_shapes(cuda):
+    """Seeded sweep over the streaming kernel's domain (N % 16 == 0 with >= 48 row tiles, K % 256 == 0, batch 1..8)."""
+    rng = np.random.default_rng(2024)
+    for case in range(16):
+        N = int(rng.integers(48, 200)) * 16
+        K = int(rng.integers(1, 13)) * 256
+        dtype = DTYPES[case % len(DTYPES)]
+        batch = int(rng.integers(1, 5 if dtype == torch.float32 else 9))
+        y, exact, _ = _gemv_case(cuda, dtype, N, K, batch, seed=1000 + case, bias=bool(case & 1))
+        assert y.shape == (batch, N)
+        assert normwise(y.float().cpu().numpy(), exact) <= TOL64[dtype], (N, K, batch, dtype)
+
+
+def test_gemm_tcgen05_random_shapes(cuda):
+    rng = np.random.default_rng(77)
+    for case in range(10):
+        N = int(rng.integers(1, 40)) * 8
+        K = int(rng.integers(1, 17)) * 64
+        rows = int(rng.integers(9, 400))
+        dtype = (torch.bfloat16, torch.float16)[case & 1]
+        y, ref = _gemm_case(cuda, dtype, rows, N, K, seed=300 + case, bias=bool(case & 2))
+        err = (y.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        assert err <= (4e-3 if dtype == torch.bfloat16 else 6e-4), (rows, N, K, dtype, err)
+
+
 def test_gemm_tcgen05_blocksize_128_and_repeat_is_deterministic(cuda):
     y0, ref = _gemm_case(cuda, torch.bfloat16, 77, 256, 1024, bs=128, seed=5)
     y1, _ = _gemm_case(cuda, torch.bfloat16, 77, 256, 1024, bs=128, seed=5)
