@@ -11,8 +11,13 @@
 // Operands are swapped with respect to the usual GEMM: the WEIGHT tile is the MMA's A operand
 // (M = 128 weight rows) and the activation tile is B (N = up to 256 tokens, any multiple of 16), so
 // small token counts waste no tensor-core rows and one dequantised tile serves up to 256 tokens.
-// Accumulators (128 lanes x tokens, fp32) live in TMEM, double-buffered so the epilogue of tile i
-// overlaps the main loop of tile i+1.
+// The dequantised weight tile never touches shared memory either: the dequantiser threads write it straight
+// into TENSOR MEMORY (tcgen05.st) and the MMA takes its A operand from there (tcgen05.mma with A in TMEM).
+// Shared-memory bandwidth is what bounds this kernel (128 B/clk: the MMA alone reads 48 KB of operands per
+// 64-k block in its 524 clocks), and this removes 32 of the ~104 KB per block that an A tile staged in shared
+// memory costs (16 KB written by the dequantisers + 16 KB read back by the tensor core).
+// Accumulators (128 lanes x tokens, fp32) live in TMEM too, double-buffered for token tiles <= 192 so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Warp roles of the persistent CTA (one per SM, 320 threads):
 //   warp 0      TMA producer: activation tiles [tokens x 64 k] -> shared memory (128-byte swizzle), and the
@@ -23,8 +28,8 @@
 //   warps 2-5   dequantisers: thread r owns weight row r of the tile; per 64-k block it reads its 32 packed
 //               bytes from the ring (swizzled: conflict-free), builds the 8
 //               possible magnitudes RN_T(|code_i| * absmax) once, then decodes 64 nibbles with byte
-//               permutes (PRMT as an 8-entry table, sign bit merged with one LOP3) and writes its
-//               128-byte row in the swizzled K-major layout
+//               permutes (PRMT as an 8-entry table, sign bit merged with one LOP3) and stores its row
+//               (32 columns of two 16-bit values) into the A ring in tensor memory
 //   warps 6-9   epilogue: tcgen05.ld (thread = output feature, registers = tokens), bias, convert, store
 //
 // Requirements: bitsandbytes FP4 codebook (code == NULL or FP4_B200_FLAG_CODE_IS_BNB_FP4), fp32 absmax,
@@ -42,7 +47,9 @@ namespace {
 constexpr int BW = 128;  // weight rows per tile (MMA M)
 constexpr int BK = 64;   // k per pipeline stage = one 128-byte swizzle row of 16-bit elements
 constexpr int kThreads = 320;
-constexpr uint32_t kStageA = BW * BK * 2;  // 16 KiB of dequantised weights per stage
+constexpr int kStagesA = 4;                // ring of dequantised weight tiles in tensor memory
+constexpr uint32_t kColsA = BK / 2;        // 32 TMEM columns per stage: 128 lanes x 64 k x 16 bit
+constexpr uint32_t kColA0 = 512 - kStagesA * kColsA;  // the A ring sits at the top of the 512 columns
 constexpr int kWSlots = 3;                 // ring of packed-weight boxes
 constexpr uint32_t kWBox = BW * 128;       // 128 rows x 128 packed bytes = 4 k blocks
 
@@ -77,13 +84,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(mbar)
         : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], issued by one thread for the whole CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
+// same with the A operand in tensor memory (128 lanes x 8 columns of packed 16-bit pairs per K = 16 step)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one warp stores 32 lanes x 32 columns: register j of lane l -> (lane base + l, column base + j)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
 // mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
@@ -133,25 +151,32 @@ struct Pack2<__half> {
 template <typename T, int BT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                        const __grid_constant__ Params p, int stages) {
+                        const __grid_constant__ Params p, int stagesB) {
     constexpr uint32_t kStageB = BT * BK * 2;
-    constexpr uint32_t kTmemCols = 2 * BT < 32 ? 32 : 2 * BT;  // powers of two for BT in {16,...,256}
+    constexpr uint32_t kTmemCols = 512;           // accumulators at columns [0, kAcc * BT), A ring at the top
+    constexpr uint32_t kAcc = 2 * BT <= kColA0 ? 2 : 1;  // accumulator buffers (BT <= 192: double-buffered)
+    static_assert(kAcc * BT <= kColA0, "accumulators and the A ring overlap");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t sA = smem_u32(smem);                       // [stages][128 rows][128 B]
-    const uint32_t sB = sA + (uint32_t)stages * kStageA;      // [stages][BT rows][128 B]
-    const uint32_t sW = sB + (uint32_t)stages * kStageB;      // [kWSlots][128 rows][128 B] packed weights
-    const uint32_t bars = sW + kWSlots * kWBox;  // full[stages], empty[stages], tfull[2], tempty[2], wfull[], wempty[]
-    const uint32_t full0 = bars, empty0 = bars + stages * 8, tfull0 = bars + stages * 16, tempty0 = tfull0 + 16;
+    const uint32_t sB = smem_u32(smem);                       // [stagesB][BT rows][128 B] activation tiles
+    const uint32_t sW = sB + (uint32_t)stagesB * kStageB;     // [kWSlots][128 rows][128 B] packed weights
+    const uint32_t bars = sW + kWSlots * kWBox;
+    const uint32_t fullA0 = bars, emptyA0 = fullA0 + kStagesA * 8;
+    const uint32_t fullB0 = emptyA0 + kStagesA * 8, emptyB0 = fullB0 + stagesB * 8;
+    const uint32_t tfull0 = emptyB0 + stagesB * 8, tempty0 = tfull0 + 16;
     const uint32_t wfull0 = tempty0 + 16, wempty0 = wfull0 + kWSlots * 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)stages * (kStageA + kStageB) + kWSlots * kWBox +
-                                                      stages * 16 + 32 + kWSlots * 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)stagesB * kStageB + kWSlots * kWBox +
+                                                      (kStagesA + stagesB) * 16 + 32 + kWSlots * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(full0 + s * 8, 1 + 128);  // TMA producer (with tx bytes) + 128 dequantiser threads
-            mbar_init(empty0 + s * 8, 1);       // tcgen05.commit
+        for (int s = 0; s < kStagesA; ++s) {
+            mbar_init(fullA0 + s * 8, 4);       // one arrival per dequantiser warp
+            mbar_init(emptyA0 + s * 8, 1);      // tcgen05.commit
+        }
+        for (int s = 0; s < stagesB; ++s) {
+            mbar_init(fullB0 + s * 8, 1);       // TMA producer (with tx bytes)
+            mbar_init(emptyB0 + s * 8, 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + a * 8, 1);       // tcgen05.commit after the last k block
@@ -192,10 +217,10 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                         mbar_expect_tx(wfull0 + ws * 8, kWBox);
                         tma_load_2d(sW + ws * kWBox, &tmW, (int)(kb * 32), (int)(wt * BW), wfull0 + ws * 8);
                     }
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
-                    mbar_wait(empty0 + s * 8, ph ^ 1);
-                    mbar_expect_tx(full0 + s * 8, kStageB);
-                    tma_load_2d(sB + s * kStageB, &tmX, (int)(kb * BK), (int)(tt * BT), full0 + s * 8);
+                    const uint32_t s = it % stagesB, ph = (it / stagesB) & 1;
+                    mbar_wait(emptyB0 + s * 8, ph ^ 1);
+                    mbar_expect_tx(fullB0 + s * 8, kStageB);
+                    tma_load_2d(sB + s * kStageB, &tmX, (int)(kb * BK), (int)(tt * BT), fullB0 + s * 8);
                 }
             }
         }
@@ -207,27 +232,32 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                                        ((uint32_t)(BW >> 4) << 24);
             uint32_t it = 0, tcount = 0;
             for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
                 mbar_wait(tempty0 + acc * 8, aph ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BT;
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
-                    mbar_wait(full0 + s * 8, ph);
+                    const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
+                    const uint32_t sb = it % stagesB, phb = (it / stagesB) & 1;
+                    mbar_wait(fullA0 + sa * 8, pha);
+                    mbar_wait(fullB0 + sb * 8, phb);
                     tc_fence_after();
-                    const uint64_t da = make_desc(sA + s * kStageA), db = make_desc(sB + s * kStageB);
+                    const uint32_t ta = tmem_base + kColA0 + sa * kColsA;
+                    const uint64_t db = make_desc(sB + sb * kStageB);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)  // 16 elements = 32 bytes along K inside the swizzle row
-                        umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(empty0 + s * 8);  // frees the stage once these MMAs have read it
+                    for (int k = 0; k < BK / 16; ++k)  // 16 elements along K: 8 TMEM columns of A, 32 bytes of the B row
+                        umma_f16_ts(tmem_d, ta + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(emptyA0 + sa * 8);  // frees the stages once these MMAs have read them
+                    umma_commit(emptyB0 + sb * 8);
                 }
                 umma_commit(tfull0 + acc * 8);  // accumulator complete
             }
         }
     } else if (warp < 6) {
         // ===== dequantisers: thread r = weight row r of the tile =====
-        const int r = threadIdx.x - 64;
+        const int r = (warp & 3) * 32 + lane;  // warp w may only touch TMEM lanes 32 (w % 4) .. +31
         const uint32_t srow = (uint32_t)r * 128, sx = (uint32_t)(r & 7);
+        const uint32_t ta_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColA0;
         float mag[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mag[i] = kBnbMag[i];
@@ -266,7 +296,7 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
                 for (int i = 0; i < PD; ++i) {
                     if (kb0 + i < nkb) {
-                        const uint32_t s = it % stages, ph = (it / stages) & 1;
+                        const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
                         ++it;
                         // this row's 32 packed bytes of the k block: 16-byte chunks 2i, 2i+1 of the swizzled row
                         uint4 qa, qb;
@@ -286,15 +316,13 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                         const uint32_t lo_a = prmt(p01, p23, 0x6420u), hi_a = prmt(p01, p23, 0x7531u);
                         const uint32_t lo_b = prmt(p45, p67, 0x6420u), hi_b = prmt(p45, p67, 0x7531u);
                         const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                        mbar_wait(empty0 + s * 8, ph ^ 1);
-                        const uint32_t dst = sA + s * kStageA + srow;
+                        uint32_t o[32];  // the row: column j = elements (2j, 2j+1)
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             // word c = 8 nibbles = elements 8c..8c+7; nibble j of the word is element j ^ 1
                             const uint32_t ww = w[c];
                             const uint32_t wm = ww & 0x77777777u, w4 = ww * 16u;
                             const uint32_t wmh = __umulhi(wm, 65536u);
-                            uint32_t o[4];
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const uint32_t sel = h ? wmh : wm;
@@ -302,16 +330,17 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                                 // sign-replicate mode: 0xFF where the nibble's sign bit is set
                                 const uint32_t sg = prmt(ww, w4, h ? 0xBFAEu : 0x9D8Cu);
                                 const uint32_t hi4 = prmt(hi_a, hi_b, sel) | (sg & 0x80808080u);
-                                o[2 * h] = prmt(lo4, hi4, 0x4051u);      // elements (0,1) of the group: nibbles (1,0)
-                                o[2 * h + 1] = prmt(lo4, hi4, 0x6273u);  // elements (2,3): nibbles (3,2)
+                                o[4 * c + 2 * h] = prmt(lo4, hi4, 0x4051u);      // elements (0,1) of the group: nibbles (1,0)
+                                o[4 * c + 2 * h + 1] = prmt(lo4, hi4, 0x6273u);  // elements (2,3): nibbles (3,2)
                             }
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)c ^ sx) << 4)),
-                                         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
-                                         : "memory");
                         }
-                        // make the generic-proxy stores visible to the tensor core (async proxy), then signal
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(full0 + s * 8);
+                        mbar_wait(emptyA0 + s * 8, ph ^ 1);  // the MMAs that read this A stage have completed
+                        tc_fence_after();
+                        tmem_st_32x32(ta_lane + s * kColsA, o);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fullA0 + s * 8);
                     }
                 }
                 mbar_arrive(wempty0 + ws * 8);  // this thread has read its row of the box
@@ -325,7 +354,7 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         T* out = reinterpret_cast<T*>(p.out);
         uint32_t tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-            const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+            const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
             const uint32_t tt = tile % p.tiles_t, wt = tile / p.tiles_t;
             const uint32_t row = wt * BW + (uint32_t)r;
             const bool row_ok = row < (uint32_t)p.N;
@@ -412,13 +441,13 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
             return FP4_B200_ERR_UNSUPPORTED;
     }
     constexpr uint32_t kStageB = BT * BK * 2;
-    int stages = (int)((196 * 1024 - kWSlots * kWBox) / (kStageA + kStageB));
-    if (stages > 6) stages = 6;
-    const size_t smem = (size_t)stages * (kStageA + kStageB) + kWSlots * kWBox + stages * 16 + 32 + kWSlots * 16 + 64 + 1024;
+    int stagesB = (int)((220 * 1024 - kWSlots * kWBox) / kStageB);
+    if (stagesB > 8) stagesB = 8;
+    const size_t smem = (size_t)stagesB * kStageB + kWSlots * kWBox + (kStagesA + stagesB) * 16 + 32 + kWSlots * 16 + 64 + 1024;
     auto kern = gemm_fp4_tcgen05_kernel<T, BT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -429,7 +458,7 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     p.tiles_t = ((uint32_t)M + BT - 1) / BT;
     p.num_tiles = p.tiles_t * (((uint32_t)N + BW - 1) / BW);
     const uint32_t grid = p.num_tiles < (uint32_t)kNumSMs ? p.num_tiles : (uint32_t)kNumSMs;
-    kern<<<grid, kThreads, smem, st>>>(tmX, tmW, p, stages);
+    kern<<<grid, kThreads, smem, st>>>(tmX, tmW, p, stagesB);
     return (int)cudaGetLastError();
 }
 
@@ -441,6 +470,9 @@ static int launch_bt(const void* x, const uint8_t* packed, const float* absmax, 
     if (M <= 32) return FP4_GO(32);
     if (M <= 64) return FP4_GO(64);
     if (M <= 128) return FP4_GO(128);
+    // 256-token tiles fill TMEM with ONE accumulator (epilogue not overlapped); 192-token tiles leave room for
+    // two.  Many token tiles: take the overlap; few: avoid the padding of 192
+    if (M >= 1536) return FP4_GO(192);
     return FP4_GO(256);
 #undef FP4_GO
 }
