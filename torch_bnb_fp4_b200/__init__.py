@@ -36,7 +36,7 @@ T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
 GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
-GEMM_MAX_ROWS = 384     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
+GEMM_MAX_ROWS = 512     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
 
 
 class ScalarType(Enum):

@@ -470,9 +470,8 @@ static int launch_bt(const void* x, const uint8_t* packed, const float* absmax, 
     if (M <= 32) return FP4_GO(32);
     if (M <= 64) return FP4_GO(64);
     if (M <= 128) return FP4_GO(128);
-    // 256-token tiles fill TMEM with ONE accumulator (epilogue not overlapped); 192-token tiles leave room for
-    // two.  Many token tiles: take the overlap; few: avoid the padding of 192
-    if (M >= 1536) return FP4_GO(192);
+    // 256-token tiles fill TMEM with ONE accumulator (the epilogue is not overlapped); 192-token tiles with two
+    // accumulators measured slower (padding + smaller MMAs), so they are not used
     return FP4_GO(256);
 #undef FP4_GO
 }
