@@ -445,7 +445,7 @@ def run_reference(args, rank, world):
                      "tok_per_s": cb["value"] * 1e9 / nbytes, "cpu_baseline": cb,
                      "config": {"workload": "CPU oracle port (reference CUDA extension not available): " + cb["sample"]},
                      "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base))
+        emit(json.dumps(base))
         return
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -506,7 +506,7 @@ def run_reference(args, rank, world):
                                   "arm runs its CUDA extension on the GPU (see DESIGN.md)"},
                  "e2e": {"value": nbytes * args.steps / t_e2e / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_e2e,
                          "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2}})
-    print(json.dumps(base))
+    emit(json.dumps(base))
 
 
 def main():
