@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark of the FP4 Linear hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mistral7b|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mistral7b|c1|llama70b] [--tp-mode peer|nccl]
 
 Workload (BASELINE.json configs[2], the one the metric is quoted on): the Mistral-7B linear stack at
 batch 1 - 32 layers x {q 4096x4096, k 1024x4096, v 1024x4096, o 4096x4096, gate 14336x4096,
@@ -16,8 +16,15 @@ timed with CUDA events around K CUDA-graph replays.  `tok_per_s` = steps / time.
 e2e: the same through the public API (TorchFP4Linear modules under GraphedCallable) with, every step,
 the host->device copy of the input activation from pinned memory and the device->host read of the
 result inside the timed region.
-N > 1 (torchrun): tensor parallel, Megatron style - q/k/v/gate/up column-parallel, o/down row-parallel
-with an all-reduce after each (2 per layer) - strong scaling of the same workload.
+grouped_launches: the same stack with q/k/v and gate/up each issued as ONE grouped launch (TorchFP4LinearGroup /
+fp4_b200_gemv_grouped; 128 launches per token) - an extension the reference does not have, reported beside
+the headline, never instead of it.
+N > 1 (torchrun): tensor parallel, Megatron style - q/k/v/gate/up column-parallel, o/down row-parallel - strong
+scaling of the same workload.  --tp-mode peer (default): the row-parallel partial sums are pushed into every
+rank's symmetric-memory buffer by the GEMV itself and summed while the next launch stages x (PeerExchange /
+fp4_b200_gemv_grouped_tp): no collective launches except one all_reduce per token for the final hidden state;
+the NCCL all_reduce-per-layer variant is timed in the same run and reported as `nccl_allreduce_variant`.
+--workload llama70b: BASELINE config #4 shapes (80 layers, 38.5 GB of FP4 linears), for reference.
 
 --impl reference: the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference/csrc)
 driven eagerly exactly as its Python module drives it (gemv_fp4 per layer on the legacy stream; it

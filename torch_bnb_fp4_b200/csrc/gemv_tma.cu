@@ -1,4 +1,5 @@
-// Fused dequant + GEMV for decode (batch 1..8) on sm_100a — TMA-staged variant (the default fast path).
+// Fused dequant + GEMV for decode (batch 1..8) on sm_100a — TMA-staged stream-K variant (fp16 tensor-core decode).
+// Superseded as the default by gemv_stream.cu; kept as a fallback for shapes outside that kernel's domain.
 //
 // Same arithmetic and the same warp-granular stream-K schedule / deterministic combine as gemv_imma.cu
 // (see there and gemv_common.cuh); what changes is how the weight stream reaches the SM.
