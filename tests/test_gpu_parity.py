@@ -326,6 +326,20 @@ def test_module_dispatch_uses_gemm_for_prefill(cuda):
     assert (y.float() - ref).abs().max().item() / ref.abs().max().item() <= 4e-3
 
 
+def test_module_uses_gemm_when_x_does_not_fit_the_gemv(cuda):
+    """8 rows x K = 14336 is too much x for the streaming GEMV's shared memory: the dispatcher takes the GEMM."""
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    torch.manual_seed(9)
+    w = (torch.randn(256, 14336) * 0.02).to(cuda)
+    m = torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w))
+    x = torch.randn(8, 14336, device=cuda, dtype=torch.bfloat16)
+    y = m(x)
+    ref = torch.nn.functional.linear(x.float(), m.quant_data.dequantize().float())
+    assert y.shape == (8, 256)
+    assert (y.float() - ref).abs().max().item() / ref.abs().max().item() <= 4e-3
+
+
 # ---------------------------------------------------------------- against the reference extension itself
 def _ref_ext():
     from oracle.build_ref import load_module
@@ -368,6 +382,13 @@ def test_against_reference_extension_live(cuda):
         # the reference's GEMM path (dequant + F.linear, fp32 accumulate) is the same mathematical op
         rg = torch.nn.functional.linear(x, r).float().cpu().numpy()
         assert normwise(oy, rg) <= 1e-2
+        if dtype != torch.float32:
+            # prefill: the reference's own pair (its dequant kernel + ATen linear, torch_bnb_fp4/__init__.py:423-436)
+            # against the dequant-fused tcgen05 GEMM, same inputs
+            xm = torch.randn(200, K, generator=torch.Generator().manual_seed(43)).to(dtype).to(cuda)
+            rgm = torch.nn.functional.linear(xm, r).float()
+            ogm = ext.gemm_fp4(xm, A, am, code, N, K, bs).float()
+            assert (ogm - rgm).abs().max().item() <= 2.0 ** -7 * rgm.abs().max().item()
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz"))) or [None])

@@ -35,6 +35,7 @@ from .ext import ScalarType as ScalarType_
 T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
+GEMV_X_SMEM_BYTES = 150 * 1024  # x terms the streaming GEMV can stage next to one ring slot per warp
 GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
 GEMM_MAX_ROWS = 512     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
 
@@ -216,12 +217,17 @@ class QuantData:
         if A.dtype != self.o_type:
             self.set_compute_type(A)
         rows = n_el // k
+        gemm_ok = (self.nested is None and self._code_is_std
+                   and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype))
         if rows <= GEMV_MAX_BATCH and k % 32 == 0 and self.blocksize % 32 == 0:
-            if not A.is_contiguous():
-                A = A.contiguous()
-            return self._qgemv(A)
-        if (GEMM_MIN_ROWS <= rows <= GEMM_MAX_ROWS and self.nested is None and self._code_is_std
-                and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype)):
+            # the streaming GEMV keeps x (as integer terms) in shared memory: rows * K * 2 bytes for 16-bit
+            # inputs.  Where that does not fit (e.g. 8 rows x K = 14336) the tensor-core GEMM with a 16-token tile
+            # is several times faster than the stream-K fallback
+            if not (rows > 2 and gemm_ok and rows * k * 2 > GEMV_X_SMEM_BYTES):
+                if not A.is_contiguous():
+                    A = A.contiguous()
+                return self._qgemv(A)
+        if rows <= GEMM_MAX_ROWS and gemm_ok:
             if not A.is_contiguous():
                 A = A.contiguous()
             return self._qgemm(A)
