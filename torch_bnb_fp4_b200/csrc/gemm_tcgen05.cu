@@ -47,7 +47,7 @@ namespace {
 constexpr int BW = 128;  // weight rows per tile (MMA M)
 constexpr int BK = 64;   // k per pipeline stage = one 128-byte swizzle row of 16-bit elements
 constexpr int kThreads = 320;
-constexpr int kStagesA = 4;                // ring of dequantised weight tiles in tensor memory
+constexpr int kStagesA = 8;                // ring of dequantised weight tiles in tensor memory
 constexpr uint32_t kColsA = BK / 2;        // 32 TMEM columns per stage: 128 lanes x 64 k x 16 bit
 constexpr uint32_t kColA0 = 512 - kStagesA * kColsA;  // the A ring sits at the top of the 512 columns
 constexpr int kWSlots = 3;                 // ring of packed-weight boxes
@@ -102,6 +102,57 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
           "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
           "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) variant: one MMA of M = 256 spans two SMs; each CTA supplies its 128 weight rows
+// (A, tensor memory) and HALF of the activation tile (B, shared memory), which halves the per-SM shared-memory
+// traffic of the operand that bounds the 1-CTA kernel.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {  // same offset in CTA `rank`'s smem
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// bounded wait with cluster-scope acquire; gives up (sets *failed) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity, volatile uint32_t* failed) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!ok && (++spins > (1u << 22) || *failed)) {
+            *failed = 1u;
+            return;
+        }
+    } while (!ok);
+}
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t mbar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(mbar), "h"((unsigned short)3)
         : "memory");
 }
 // mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
@@ -394,6 +445,269 @@ gemm_fp4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
 }
 
+
+// CTA-pair kernel: cluster of 2; pair tile = 256 weight rows x 256 tokens.  CTA `rank` owns weight rows
+// [256 wt2 + 128 rank, +128) (dequantised into ITS tensor memory) and tokens [256 tt + 128 rank, +128) (TMA into ITS
+// shared memory).  The leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256, N = 256); the hardware reads A
+// from both CTAs' TMEM and B from both CTAs' shared memory and leaves each CTA's 128 x 256 accumulator in its
+// own TMEM.  Cross-CTA signalling: the peer's dequantiser warps arrive on the leader's fullA barriers, its
+// idle "MMA" lane relays its activation-tile arrivals to the leader, its epilogue arrives on the leader's
+// tempty; tcgen05.commit multicasts to both CTAs' empty / tfull barriers.
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_fp4_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                             const __grid_constant__ Params p, int stagesB, uint32_t* gfailed) {
+    constexpr int BT = 256, BTH = 128;            // tokens per pair tile / per CTA
+    constexpr uint32_t kStageB = BTH * BK * 2;    // 16 KiB: this CTA's half of the activation tile
+    constexpr uint32_t kTmemCols = 512;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sB = smem_u32(smem);
+    const uint32_t sW = sB + (uint32_t)stagesB * kStageB;
+    const uint32_t bars = sW + kWSlots * kWBox;
+    const uint32_t fullA0 = bars, emptyA0 = fullA0 + kStagesA * 8;
+    const uint32_t fullB0 = emptyA0 + kStagesA * 8, emptyB0 = fullB0 + stagesB * 8;
+    const uint32_t peerB0 = emptyB0 + stagesB * 8;  // leader only: the peer's half of stage s has landed
+    const uint32_t tfull0 = peerB0 + stagesB * 8, tempty0 = tfull0 + 16;
+    const uint32_t wfull0 = tempty0 + 16, wempty0 = wfull0 + kWSlots * 8;
+    uint8_t* tail = smem + (size_t)stagesB * kStageB + kWSlots * kWBox + kStagesA * 16 + stagesB * 24 + 32 + kWSlots * 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
+    volatile uint32_t* failed = reinterpret_cast<volatile uint32_t*>(tail + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    if (threadIdx.x == 0) {
+        *failed = 0u;
+        for (int s = 0; s < kStagesA; ++s) {
+            mbar_init(fullA0 + s * 8, 8);       // 4 dequantiser warps of each CTA (counted in the leader)
+            mbar_init(emptyA0 + s * 8, 1);      // multicast tcgen05.commit
+        }
+        for (int s = 0; s < stagesB; ++s) {
+            mbar_init(fullB0 + s * 8, 1);       // this CTA's TMA (with tx bytes)
+            mbar_init(emptyB0 + s * 8, 1);      // multicast tcgen05.commit
+            mbar_init(peerB0 + s * 8, 1);       // relay from the peer
+        }
+        mbar_init(tfull0, 1);                   // multicast tcgen05.commit after the last k block
+        mbar_init(tempty0, 256);                // epilogue threads of both CTAs (counted in the leader)
+        for (int w = 0; w < kWSlots; ++w) {
+            mbar_init(wfull0 + w * 8, 1);
+            mbar_init(wempty0 + w * 8, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    }
+    if (warp == 1) {  // collective over the pair: one warp of each CTA
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // both CTAs' barriers are initialised before anyone signals across
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t nkb = p.nkb;
+    const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's packed weight boxes and its half of the activation tile =====
+        if (lane == 0) {
+            uint32_t it = 0, wit = 0;
+            for (uint32_t tile = pair; tile < p.num_tiles && !*failed; tile += npairs) {
+                const uint32_t tt = tile % p.tiles_t, wt = (tile / p.tiles_t) * 2 + rank;
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    if ((kb & 3) == 0) {
+                        const uint32_t ws = wit % kWSlots, wph = (wit / kWSlots) & 1;
+                        ++wit;
+                        mbar_wait_cluster(wempty0 + ws * 8, wph ^ 1, failed);
+                        mbar_expect_tx(wfull0 + ws * 8, kWBox);
+                        tma_load_2d(sW + ws * kWBox, &tmW, (int)(kb * 32), (int)(wt * BW), wfull0 + ws * 8);
+                    }
+                    const uint32_t s = it % stagesB, ph = (it / stagesB) & 1;
+                    mbar_wait_cluster(emptyB0 + s * 8, ph ^ 1, failed);
+                    mbar_expect_tx(fullB0 + s * 8, kStageB);
+                    tma_load_2d(sB + s * kStageB, &tmX, (int)(kb * BK), (int)(tt * BT + rank * BTH), fullB0 + s * 8);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader) =====
+            constexpr uint32_t fmt = sizeof(T) == 2 && DT<T>::code == FP4_B200_BF16 ? 1u : 0u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BT >> 3) << 17) |
+                                       ((uint32_t)(256 >> 4) << 24);
+            uint32_t it = 0, tcount = 0;
+            for (uint32_t tile = pair; tile < p.num_tiles && !*failed; tile += npairs, ++tcount) {
+                mbar_wait_cluster(tempty0, (tcount & 1) ^ 1, failed);  // both epilogues have drained the accumulator
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
+                    const uint32_t sb = it % stagesB, phb = (it / stagesB) & 1;
+                    mbar_wait_cluster(fullA0 + sa * 8, pha, failed);
+                    mbar_wait_cluster(fullB0 + sb * 8, phb, failed);
+                    mbar_wait_cluster(peerB0 + sb * 8, phb, failed);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + kColA0 + sa * kColsA;
+                    const uint64_t db = make_desc(sB + sb * kStageB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_ts_pair(tmem_base, ta + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit_pair(emptyA0 + sa * 8);
+                    umma_commit_pair(emptyB0 + sb * 8);
+                }
+                umma_commit_pair(tfull0);
+            }
+        } else if (lane == 0 && rank == 1) {
+            // ===== relay (peer): tell the leader that this CTA's half of stage s has landed =====
+            uint32_t it = 0;
+            for (uint32_t tile = pair; tile < p.num_tiles && !*failed; tile += npairs) {
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t sb = it % stagesB, phb = (it / stagesB) & 1;
+                    mbar_wait_cluster(fullB0 + sb * 8, phb, failed);
+                    mbar_arrive_cluster(map_to_cta(peerB0 + sb * 8, 0));
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===== dequantisers (as in the 1-CTA kernel; arrivals go to the leader's fullA) =====
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t srow = (uint32_t)r * 128, sx = (uint32_t)(r & 7);
+        const uint32_t ta_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColA0;
+        float mag[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mag[i] = kBnbMag[i];
+        uint32_t it = 0, wit = 0;
+        constexpr int PD = 4;
+        float am[PD];
+        uint32_t ld_tile = pair, ld_kb0 = 0;
+        auto load_box_absmax = [&]() {
+            if (ld_tile < p.num_tiles) {
+                const uint32_t wt = (ld_tile / p.tiles_t) * 2 + rank;
+                uint32_t row = wt * BW + (uint32_t)r;
+                row = row < (uint32_t)p.N ? row : (uint32_t)p.N - 1;
+                const size_t b0 = (size_t)row * nkb + ld_kb0;
+#pragma unroll
+                for (int i = 0; i < PD; ++i)
+                    if (ld_kb0 + i < nkb) am[i] = __ldg(p.absmax + ((b0 + i) >> p.bs_shift));
+                ld_kb0 += PD;
+                if (ld_kb0 >= nkb) {
+                    ld_kb0 = 0;
+                    ld_tile += npairs;
+                }
+            }
+        };
+        load_box_absmax();
+        for (uint32_t tile = pair; tile < p.num_tiles && !*failed; tile += npairs) {
+            for (uint32_t kb0 = 0; kb0 < nkb; kb0 += PD) {
+                const uint32_t ws = wit % kWSlots, wph = (wit / kWSlots) & 1;
+                ++wit;
+                mbar_wait_cluster(wfull0 + ws * 8, wph, failed);
+                const uint32_t wsrc = sW + ws * kWBox + srow;
+                float amc[PD];
+#pragma unroll
+                for (int i = 0; i < PD; ++i) amc[i] = am[i];
+                load_box_absmax();
+#pragma unroll
+                for (int i = 0; i < PD; ++i) {
+                    if (kb0 + i < nkb) {
+                        const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
+                        ++it;
+                        uint4 qa, qb;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(qa.x), "=r"(qa.y), "=r"(qa.z), "=r"(qa.w)
+                                     : "r"(wsrc + (((uint32_t)(2 * i) ^ sx) << 4)));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(qb.x), "=r"(qb.y), "=r"(qb.z), "=r"(qb.w)
+                                     : "r"(wsrc + (((uint32_t)(2 * i + 1) ^ sx) << 4)));
+                        const float a_ = amc[i];
+                        const uint32_t p01 = Pack2<T>::go(__fmul_rn(mag[0], a_), __fmul_rn(mag[1], a_));
+                        const uint32_t p23 = Pack2<T>::go(__fmul_rn(mag[2], a_), __fmul_rn(mag[3], a_));
+                        const uint32_t p45 = Pack2<T>::go(__fmul_rn(mag[4], a_), __fmul_rn(mag[5], a_));
+                        const uint32_t p67 = Pack2<T>::go(__fmul_rn(mag[6], a_), __fmul_rn(mag[7], a_));
+                        const uint32_t lo_a = prmt(p01, p23, 0x6420u), hi_a = prmt(p01, p23, 0x7531u);
+                        const uint32_t lo_b = prmt(p45, p67, 0x6420u), hi_b = prmt(p45, p67, 0x7531u);
+                        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                        uint32_t o[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t ww = w[c];
+                            const uint32_t wm = ww & 0x77777777u, w4 = ww * 16u;
+                            const uint32_t wmh = __umulhi(wm, 65536u);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t sel = h ? wmh : wm;
+                                const uint32_t lo4 = prmt(lo_a, lo_b, sel);
+                                const uint32_t sg = prmt(ww, w4, h ? 0xBFAEu : 0x9D8Cu);
+                                const uint32_t hi4 = prmt(hi_a, hi_b, sel) | (sg & 0x80808080u);
+                                o[4 * c + 2 * h] = prmt(lo4, hi4, 0x4051u);
+                                o[4 * c + 2 * h + 1] = prmt(lo4, hi4, 0x6273u);
+                            }
+                        }
+                        mbar_wait_cluster(emptyA0 + s * 8, ph ^ 1, failed);
+                        tc_fence_after();
+                        tmem_st_32x32(ta_lane + s * kColsA, o);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(map_to_cta(fullA0 + s * 8, 0));
+                    }
+                }
+                mbar_arrive(wempty0 + ws * 8);
+            }
+        }
+    } else {
+        // ===== epilogue: this CTA's 128 weight rows x 256 tokens =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const T* bias = reinterpret_cast<const T*>(p.bias);
+        T* out = reinterpret_cast<T*>(p.out);
+        const uint32_t tempty_leader = map_to_cta(tempty0, 0);
+        uint32_t tcount = 0;
+        for (uint32_t tile = pair; tile < p.num_tiles && !*failed; tile += npairs, ++tcount) {
+            const uint32_t tt = tile % p.tiles_t, wt = (tile / p.tiles_t) * 2 + rank;
+            const uint32_t row = wt * BW + (uint32_t)r;
+            const bool row_ok = row < (uint32_t)p.N;
+            const float bv = (bias && row_ok) ? DT<T>::to_f32(bias[row]) : 0.f;
+            mbar_wait_cluster(tfull0, tcount & 1, failed);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BT; c0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15])
+                    : "r"(taddr + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t tok0 = tt * BT + c0;
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t tok = tok0 + j;
+                        if (tok < (uint32_t)p.M) out[(size_t)tok * p.N + row] = DT<T>::from_f32(__uint_as_float(v[j]) + bv);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty_leader);
+        }
+    }
+
+    if (threadIdx.x == 0 && *failed) *gfailed = 1u;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // neither CTA frees tensor memory (or exits) while the other may still use the pair
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -462,6 +776,74 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     return (int)cudaGetLastError();
 }
 
+
+// CTA-pair launch (M > 128 tokens): returns FP4_B200_ERR_UNSUPPORTED when switched off or not applicable
+template <typename T>
+static int launch_pair(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out, int M,
+                       int N, int K, int bs_shift, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return FP4_B200_ERR_UNSUPPORTED;
+    CUtensorMap tmX, tmW;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUtensorMapDataType dt =
+            DT<T>::code == FP4_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        if (enc(&tmX, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FP4_B200_ERR_UNSUPPORTED;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)K / 2, (cuuint64_t)N};
+        const cuuint64_t strides[1] = {(cuuint64_t)K / 2};
+        const cuuint32_t box[2] = {128, (cuuint32_t)BW};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(packed), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FP4_B200_ERR_UNSUPPORTED;
+    }
+    constexpr uint32_t kStageB = 128 * BK * 2;
+    int stagesB = (int)((200 * 1024 - kWSlots * kWBox) / kStageB);
+    if (stagesB > 8) stagesB = 8;
+    const size_t smem = (size_t)stagesB * kStageB + kWSlots * kWBox + kStagesA * 16 + stagesB * 24 + 32 + kWSlots * 16 +
+                        64 + 1024;
+    auto kern = gemm_fp4_tcgen05_pair_kernel<T>;
+    static bool configured = false;
+    static uint32_t* gfailed = nullptr;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (cudaMalloc(&gfailed, 4) != cudaSuccess) return FP4_B200_ERR_UNSUPPORTED;
+        cudaMemset(gfailed, 0, 4);
+        configured = true;
+    }
+    Params p;
+    p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;
+    p.M = M; p.N = N; p.K = K; p.bs_shift = bs_shift;
+    p.nkb = (uint32_t)K / BK;
+    p.tiles_t = ((uint32_t)M + 255) / 256;
+    p.num_tiles = p.tiles_t * (((uint32_t)N + 255) / 256);
+    const uint32_t pairs = p.num_tiles < (uint32_t)kNumSMs / 2 ? p.num_tiles : (uint32_t)kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pairs * 2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p, stagesB, gfailed);
+}
+
 template <typename T>
 static int launch_bt(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out, int M,
                      int N, int K, int bs_shift, cudaStream_t st) {
@@ -470,6 +852,8 @@ static int launch_bt(const void* x, const uint8_t* packed, const float* absmax, 
     if (M <= 32) return FP4_GO(32);
     if (M <= 64) return FP4_GO(64);
     if (M <= 128) return FP4_GO(128);
+    static const int pair_min = getenv("FP4_B200_GEMM_PAIR_MIN_M") ? atoi(getenv("FP4_B200_GEMM_PAIR_MIN_M")) : (1 << 30);
+    if (M >= pair_min) return launch_pair<T>(x, packed, absmax, bias, out, M, N, K, bs_shift, st);
     // 256-token tiles fill TMEM with ONE accumulator (the epilogue is not overlapped); 192-token tiles with two
     // accumulators measured slower (padding + smaller MMAs), so they are not used
     return FP4_GO(256);
