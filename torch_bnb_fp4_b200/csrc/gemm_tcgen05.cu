@@ -122,14 +122,16 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) { 
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// bounded wait with cluster-scope acquire; gives up (sets *failed) instead of hanging the GPU
+// bounded wait; gives up (sets *failed) instead of hanging the GPU.  Default (CTA-scope) semantics as in CUTLASS'
+// ClusterBarrier: a cluster-scope acquire costs an L1 invalidate (CCTL.IVALL) per poll and is not needed, the
+// data handed over lives in tensor memory / the async proxy (tcgen05 fences order it)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity, volatile uint32_t* failed) {
     uint32_t ok, spins = 0;
     do {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(a), "r"(parity)
