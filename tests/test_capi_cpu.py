@@ -45,3 +45,24 @@ def test_status_strings_and_early_validation():
     assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 48, 0, None) == -4
     assert lib.fp4_b200_dequantize(1, 1, None, 1, 16, 64, 9, None) == -2
     assert lib.fp4_b200_dequantize(1, 1, None, 1, 0, 64, 0, None) == 0                      # empty
+
+
+def test_tp_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of fp4_b200_tp_t / fp4_b200_nested_t has the C layout (compiled with gcc from the header)."""
+    import subprocess
+
+    from torch_bnb_fp4_b200 import _lib
+
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fp4_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fp4_b200_tp_t),'
+                   'offsetof(fp4_b200_tp_t,in_base),offsetof(fp4_b200_tp_t,slot_bytes),offsetof(fp4_b200_tp_t,out_world),'
+                   'offsetof(fp4_b200_tp_t,out_peer_base),offsetof(fp4_b200_tp_t,epochs),offsetof(fp4_b200_tp_t,err),'
+                   'sizeof(fp4_b200_nested_t));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    T = _lib.TpExchange
+    want = [ctypes.sizeof(T), T.in_base.offset, T.slot_bytes.offset, T.out_world.offset, T.out_peer_base.offset,
+            T.epochs.offset, T.err.offset, ctypes.sizeof(_lib.Nested)]
+    assert got == want
