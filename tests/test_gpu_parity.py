@@ -340,6 +340,24 @@ def test_module_uses_gemm_when_x_does_not_fit_the_gemv(cuda):
     assert (y.float() - ref).abs().max().item() / ref.abs().max().item() <= 4e-3
 
 
+def test_quantized_state_dict_round_trip(cuda):
+    """Save a layer with the bitsandbytes 4-bit keys, reload it, same outputs bit for bit (plain and nested)."""
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    torch.manual_seed(12)
+    w = (torch.randn(1024, 512) * 0.05).to(cuda)
+    b = (torch.randn(1024) * 0.1).to(cuda)
+    for nested in (False, True):
+        m = torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w, b, compress_statistics=nested))
+        sd = {k: v.cpu() for k, v in m.quantized_state_dict("layers.0.q_proj.").items()}
+        assert "layers.0.q_proj.weight.quant_state.bitsandbytes__fp4" in sd
+        assert ("layers.0.q_proj.weight.nested_absmax" in sd) == nested
+        m2 = torch_bnb_fp4.TorchFP4Linear.from_quantized_state_dict(sd, "layers.0.q_proj.", device=cuda)
+        for rows in (1, 40):
+            x = torch.randn(rows, 512, device=cuda, dtype=torch.bfloat16)
+            assert torch.equal(m(x), m2(x))
+
+
 # ---------------------------------------------------------------- against the reference extension itself
 def _ref_ext():
     from oracle.build_ref import load_module

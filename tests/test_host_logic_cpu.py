@@ -72,3 +72,33 @@ def test_name_filter_and_dynamic_map():
 def test_surgery_requires_cuda_device():
     with pytest.raises(AssertionError):
         torch_bnb_fp4.recursively_replace_with_fp4_linear(torch.nn.Linear(8, 8), device=torch.device("cpu"))
+
+
+def test_bnb_4bit_serialisation_round_trip_cpu():
+    """QuantState <-> the bitsandbytes 4-bit state_dict keys, plain and nested."""
+    import torch
+    from torch_bnb_fp4_b200 import bnb_compat as bc
+
+    code = bc.FP4_CODE.clone()
+    plain = bc.QuantState(absmax=torch.rand(32), shape=(16, 128), code=code, blocksize=64, quant_type="fp4",
+                          dtype=torch.bfloat16)
+    d = bc.quant_state_as_dict(plain, packed=True)
+    assert set(d) == {"absmax", "quant_map", "quant_state.bitsandbytes__fp4"}
+    assert d["quant_state.bitsandbytes__fp4"].dtype == torch.uint8
+    meta = bc._unpack_tensor_to_dict(d["quant_state.bitsandbytes__fp4"])
+    assert meta == {"quant_type": "fp4", "blocksize": 64, "dtype": "bfloat16", "shape": [16, 128]}
+    back = bc.quant_state_from_dict(d)
+    assert torch.equal(back.absmax, plain.absmax) and torch.equal(back.code, code)
+    assert tuple(back.shape) == (16, 128) and back.blocksize == 64 and back.dtype == torch.bfloat16 and not back.nested
+
+    state2 = bc.QuantState(absmax=torch.rand(1), code=bc.create_dynamic_map(), blocksize=256, dtype=torch.float32)
+    nested = bc.QuantState(absmax=torch.randint(0, 256, (32,), dtype=torch.uint8), shape=(16, 128), code=code,
+                           blocksize=64, quant_type="fp4", dtype=torch.float16, offset=torch.tensor(0.0371),
+                           state2=state2)
+    d = bc.quant_state_as_dict(nested, packed=True)
+    assert {"nested_absmax", "nested_quant_map"} <= set(d)
+    meta = bc._unpack_tensor_to_dict(d["quant_state.bitsandbytes__fp4"])
+    assert meta["nested_blocksize"] == 256 and abs(meta["nested_offset"] - 0.0371) < 1e-6
+    back = bc.quant_state_from_dict(d)
+    assert back.nested and torch.equal(back.absmax, nested.absmax) and back.state2.blocksize == 256
+    assert torch.equal(back.state2.code, state2.code) and abs(float(back.offset) - 0.0371) < 1e-6

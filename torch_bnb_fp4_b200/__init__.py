@@ -26,6 +26,7 @@ from torch import nn
 
 from . import ext as _ext
 from ._lib import FLAG_FORCE_GENERIC  # noqa: F401
+from . import bnb_compat
 from .bnb_compat import BF, HAVE_BNB, Linear4bit, LinearFP4, Params4bit  # noqa: F401
 from .ext import (dequantize_fp4 as dequantize_fp4_, dequantize_fp4_codebook as dequantize_fp4_codebook_,
                   gemv_fp4 as gemv_fp4_, qlinear as qlinear_, qlinear_bias as qlinear_bias_,
@@ -270,6 +271,33 @@ class TorchFP4Linear(nn.Module):
         dt = f", dtype={self.quant_data.o_type}" if hasattr(self, "quant_data") else ""
         return (f"TorchFP4Linear(in_features={lin.in_features}, out_features={lin.out_features}, "
                 f"bias={lin.bias is not None}{dt})")
+
+    # -- on-disk / wire format (the reference keeps the layer in a python list and has no
+    #    state_dict at all): the keys bitsandbytes' Linear4bit writes, so checkpoints are interchangeable
+    def quantized_state_dict(self, prefix: str = "") -> dict:
+        lin = self.lin[0]
+        out = {prefix + "weight": lin.weight.data}
+        for k, v in bnb_compat.quant_state_as_dict(lin.weight.quant_state, packed=True).items():
+            out[prefix + "weight." + k] = v
+        if getattr(lin, "bias", None) is not None:
+            out[prefix + "bias"] = lin.bias.data
+        return out
+
+    @classmethod
+    def from_quantized_state_dict(cls, sd: dict, prefix: str = "", device="cuda", **kw) -> "TorchFP4Linear":
+        """Rebuild a layer from the bitsandbytes 4-bit keys (`weight`, `weight.absmax`, `weight.quant_map`,
+        `weight.quant_state.bitsandbytes__fp4`, optional `weight.nested_*`, `bias`)."""
+        w = sd[prefix + "weight"]
+        comp = {k[len(prefix) + len("weight."):]: v for k, v in sd.items() if k.startswith(prefix + "weight.")}
+        qs = bnb_compat.quant_state_from_dict(comp, device=device)
+        out_f, in_f = int(qs.shape[0]), int(qs.shape[1])
+        bias = sd.get(prefix + "bias")
+        lin = bnb_compat.LinearFP4(in_f, out_f, bias=bias is not None, compress_statistics=bool(qs.nested))
+        lin.weight = Params4bit(w.to(device).contiguous().view(-1, 1), requires_grad=False, quant_state=qs,
+                                blocksize=qs.blocksize, compress_statistics=bool(qs.nested), quant_type="fp4")
+        if bias is not None:
+            lin.bias = nn.Parameter(bias.detach().clone().to(device), requires_grad=False)
+        return cls(lin, **kw)
 
     @classmethod
     def from_linear(cls, linear, use_codebook_dequant: bool = False, name: str = "") -> "TorchFP4Linear":

@@ -195,6 +195,61 @@ if not HAVE_BNB:
     BF = _BF()
 
 
+# ---- on-disk / wire format of a bitsandbytes 4-bit weight ---------------------------
+# bitsandbytes (QuantState.as_dict(packed=True) / Linear4bit._save_to_state_dict) stores, next to the packed
+# `weight` (uint8): `weight.absmax`, `weight.quant_map` (the 16-entry code), for a double-quantised absmax also
+# `weight.nested_absmax` and `weight.nested_quant_map`, and every non-tensor field as JSON in a uint8 tensor
+# under `weight.quant_state.bitsandbytes__fp4`.  vLLM's loader reads the same keys
+# (vllm/model_executor/model_loader/bitsandbytes_loader.py).  The helpers below write and read that layout for
+# any QuantState-like object, so checkpoints saved by bitsandbytes load here and vice versa.
+def _pack_dict_to_tensor(d: dict) -> torch.Tensor:
+    import json
+
+    return torch.frombuffer(bytearray(json.dumps(d).encode("utf-8")), dtype=torch.uint8).clone()
+
+
+def _unpack_tensor_to_dict(t: torch.Tensor) -> dict:
+    import json
+
+    return json.loads(bytes(t.detach().cpu().to(torch.uint8).numpy().tobytes()).decode("utf-8"))
+
+
+def quant_state_as_dict(qs, packed: bool = True) -> dict:
+    """bitsandbytes QuantState.as_dict: tensors under their own keys, the rest as one packed JSON tensor."""
+    d = {"quant_type": qs.quant_type, "absmax": qs.absmax, "blocksize": int(qs.blocksize), "quant_map": qs.code,
+         "dtype": str(qs.dtype).replace("torch.", ""), "shape": tuple(int(v) for v in qs.shape)}
+    if getattr(qs, "nested", False):
+        off = qs.offset
+        d.update({"nested_absmax": qs.state2.absmax, "nested_blocksize": int(qs.state2.blocksize),
+                  "nested_quant_map": qs.state2.code.clone(),
+                  "nested_dtype": str(qs.state2.dtype).replace("torch.", ""),
+                  "nested_offset": float(off.item()) if torch.is_tensor(off) else float(off)})
+    if not packed:
+        return d
+    out = {k: v for k, v in d.items() if torch.is_tensor(v)}
+    rest = {k: v for k, v in d.items() if not torch.is_tensor(v)}
+    out["quant_state.bitsandbytes__" + qs.quant_type] = _pack_dict_to_tensor(rest)
+    return out
+
+
+def quant_state_from_dict(d: dict, device=None):
+    """Inverse of quant_state_as_dict (accepts the packed and the unpacked form)."""
+    d = dict(d)
+    packed_keys = [k for k in d if k.startswith("quant_state.bitsandbytes__")]
+    if packed_keys:
+        d.update(_unpack_tensor_to_dict(d.pop(packed_keys[0])))
+    mv = (lambda t: t.to(device)) if device is not None else (lambda t: t)
+    state2, offset = None, None
+    if "nested_absmax" in d:
+        offset = torch.tensor(float(d["nested_offset"]))
+        state2 = QuantState(absmax=mv(d["nested_absmax"]), blocksize=int(d["nested_blocksize"]),
+                            code=mv(d["nested_quant_map"]), dtype=getattr(torch, d["nested_dtype"]))
+        offset = mv(offset)
+    return QuantState(absmax=mv(d["absmax"]), shape=torch.Size(d["shape"]), code=mv(d["quant_map"]),
+                      blocksize=int(d["blocksize"]), quant_type=d["quant_type"], dtype=getattr(torch, d["dtype"]),
+                      offset=offset, state2=state2)
+
+
 def make_quantized_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
                           blocksize: int = 64, compress_statistics: bool = False):
     """Helper for tests/benches: an already-quantised LinearFP4 holding `weight` [out, in] (CUDA)."""
