@@ -151,10 +151,11 @@ def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N,K,batch", [(2400, 512, 1), (1024, 1536, 2), (2368, 3584, 1), (1600, 1024, 3),
                                        (1024, 1024, 4), (1024, 512, 5), (1024, 1024, 8), (4736, 512, 2),
-                                       (1024, 1792, 1), (2048, 256, 2), (1536, 768, 3)])
+                                       (1024, 1792, 1), (2048, 256, 2), (1536, 768, 3),
+                                       # block-aligned variant (more than 8 (row, term) columns): 16-bit batch
+                                       # 5..8, fp32 batch 3..8; half units, ragged tiles
+                                       (2400, 1024, 6), (1024, 768, 7), (2368, 1280, 8), (1536, 256, 5)])
 def test_gemv_stream_kernel_shapes(cuda, dtype, N, K, batch):
-    if dtype == torch.float32 and batch > 4:
-        batch = 4  # fp32 activations take 4 integer terms: the kernel covers batch <= 4, beyond that stream-K
     y, exact, _ = _gemv_case(cuda, dtype, N, K, batch, seed=N + K + batch, bias=(batch % 2 == 0))
     assert y.shape == (batch, N)
     assert normwise(y.float().cpu().numpy(), exact) <= TOL64[dtype]
@@ -206,6 +207,36 @@ def test_linear_group_module(cuda):
     xl = torch.randn(3, 20, 512, device=cuda, dtype=torch.float16)  # prefill-sized: per-layer fallback
     a, b = grp(xl)
     assert a.shape == (3, 20, 1536) and torch.equal(b, mods[1](xl))
+
+
+def test_group_projections_inside_an_unmodified_block(cuda):
+    """q_proj/k_proj/v_proj and gate_proj/up_proj of a HF-style block share launches after group_projections()."""
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            mk = lambda o, i: torch_bnb_fp4.TorchFP4Linear(  # noqa: E731
+                bnb_compat.make_quantized_linear((torch.randn(o, i) * 0.05).to(cuda)))
+            self.q_proj, self.k_proj, self.v_proj = mk(1024, 512), mk(256, 512), mk(256, 512)
+            self.gate_proj, self.up_proj, self.down_proj = mk(1536, 512), mk(1536, 512), mk(512, 1536)
+
+        def forward(self, x):
+            q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+            h = x + q[..., :512] + torch.cat([k, v], -1)
+            return self.down_proj(torch.nn.functional.silu(self.gate_proj(h)) * self.up_proj(h))
+
+    torch.manual_seed(4)
+    blk = Block()
+    x = torch.randn(1, 1, 512, device=cuda, dtype=torch.bfloat16)
+    ref = blk(x)
+    assert torch_bnb_fp4.group_projections(blk) == 2
+    got = blk(x)
+    assert (got.float() - ref.float()).abs().max().item() <= 2.0 ** -6 * ref.float().abs().max().item()
+    assert torch.equal(blk(x), got)                       # cached outputs are consumed exactly once per call
+    xl = torch.randn(2, 30, 512, device=cuda, dtype=torch.bfloat16)
+    assert blk(xl).shape == (2, 30, 512)                  # prefill-sized input: per-layer paths
 
 
 def test_gemv_custom_code_is_honoured(cuda):

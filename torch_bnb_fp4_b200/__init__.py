@@ -224,7 +224,11 @@ class QuantData:
             # the streaming GEMV keeps x (as integer terms) in shared memory: rows * K * 2 bytes for 16-bit
             # inputs.  Where that does not fit (e.g. 8 rows x K = 14336) the tensor-core GEMM with a 16-token tile
             # is several times faster than the stream-K fallback
-            if not (rows > 2 and gemm_ok and rows * k * 2 > GEMV_X_SMEM_BYTES):
+            # (fp32 inputs take four integer terms per element instead of two and have no fused GEMM: dequant +
+            # cuBLAS then, the generic GEMV is an order of magnitude slower at that size)
+            x_bytes = rows * k * (4 if A.dtype == torch.float32 else 2)
+            too_big = rows > 2 and x_bytes > GEMV_X_SMEM_BYTES
+            if not (too_big and (gemm_ok or A.dtype == torch.float32)):
                 if not A.is_contiguous():
                     A = A.contiguous()
                 return self._qgemv(A)
@@ -331,6 +335,71 @@ class TorchFP4LinearGroup(nn.Module):
             if outs is not None:
                 return tuple(outs)
         return tuple(m(x) for m in self.layers)
+
+
+class _GroupMember(nn.Module):
+    """One projection of a TorchFP4LinearGroup that is called like a plain nn.Linear: the FIRST member called with
+    a new input runs the whole group in one launch and parks the siblings' outputs; the siblings return them when
+    they are called with the same input tensor (same storage, shape and version) and fall back to their own launch
+    otherwise.  This is what lets an unmodified model (``self.q_proj(x); self.k_proj(x); self.v_proj(x)``) use
+    the grouped kernel."""
+
+    def __init__(self, group: "TorchFP4LinearGroup", index: int):
+        super().__init__()
+        self._group = [group]  # hidden from module registration: the group owns the layers
+        self.index = index
+        self.layer = group.layers[index]
+
+    @staticmethod
+    def _key(x: torch.Tensor):
+        return (x.data_ptr(), tuple(x.shape), x.dtype, x._version)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        g = self._group[0]
+        key = self._key(x)
+        if g._cache_key == key and g._cache[self.index] is not None:
+            out, g._cache[self.index] = g._cache[self.index], None
+            return out
+        rows = x.numel() // x.shape[-1] if x.shape[-1] else 0
+        if not (0 < rows <= GEMV_MAX_BATCH):
+            return self.layer(x)
+        outs = list(g(x))
+        g._cache_key = key
+        g._cache_x = x  # keeps the storage alive, so the address in the key cannot be reused by another tensor
+        g._cache = outs
+        out, g._cache[self.index] = g._cache[self.index], None
+        return out
+
+    def __getattr__(self, name):  # in_features, weight, ... resolve on the wrapped layer
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__("layer"), name)
+
+
+_GROUPABLE_NAMES = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"))
+
+
+def group_projections(model: nn.Module, names=_GROUPABLE_NAMES) -> int:
+    """Extension: find sibling TorchFP4Linear layers that read the same input in decoder blocks (q/k/v,
+    gate/up by their usual names) and make them share one grouped launch, without touching the model's
+    forward code.  Returns the number of groups created."""
+    made = 0
+    for parent in model.modules():
+        for group_names in names:
+            subs = [getattr(parent, n, None) for n in group_names]
+            if not all(isinstance(m, TorchFP4Linear) for m in subs):
+                continue
+            if len({m.in_features for m in subs}) != 1:
+                continue
+            grp = TorchFP4LinearGroup(subs)
+            grp._cache_key, grp._cache_x, grp._cache = None, None, [None] * len(subs)
+            if not grp._groupable:
+                continue
+            for i, n in enumerate(group_names):
+                setattr(parent, n, _GroupMember(grp, i))
+            made += 1
+    return made
 
 
 @torch.no_grad()

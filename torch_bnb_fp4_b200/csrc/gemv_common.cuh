@@ -99,6 +99,11 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
                  : "r"(saddr));
     return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
+    return r;
+}
 __device__ __forceinline__ uint2 lds_u2(uint32_t saddr) {
     uint2 r;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));

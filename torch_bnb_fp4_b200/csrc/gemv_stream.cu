@@ -29,6 +29,12 @@
 //     one holding x for the lanes of block A and zeros elsewhere, the other the same for block B.
 //   The contraction is unchanged (one weight row x one activation vector); the tensor core is only the
 //   multiply-add engine that takes the FMAs off the issue-limited pipes.
+//   * ALIGNED variant (more than eight (batch row, term) columns, i.e. batch >= 5 for 16-bit inputs): half of
+//     the columns above are structural zeros, and IMMA issue is what batch 3..8 is bound by.  Here the 16-byte
+//     chunks of a row are stored transposed in the ring (lane (g,t) writes slot position t*8+g) and a lane reads
+//     word t of chunk i with a 32-bit load, so the four lanes of a k-group cover ONE absmax block and every MMA
+//     column is a real (batch row, term): half the IMMAs.  x is staged in the matching order with a 16-byte
+//     row pad (conflict-free 128-bit reads).
 //
 // Row tiles are never split between CTAs (no global atomics, fences or workspace): tiles a CTA's warps
 // share are summed through shared memory in warp order after one __syncthreads (deterministic).
@@ -62,7 +68,10 @@ constexpr int kThreads = kW * 32;
 constexpr float kMagic = 12582912.f;     // 1.5 * 2^23: int32 accumulators that start at its bit pattern read as floats
 constexpr uint32_t kTabHi = 0x30206040u;  // 192*|code[4..7]| = 64, 96, 32, 48  (low half 0xC0800100 lives in a register)
 constexpr uint32_t kZeroBytes = 512;      // zero region read by the lanes of masked MMA columns
-constexpr uint32_t kMaxSmem = 226 * 1024; // per CTA: half an SM, so the next launch (PDL) is resident while this one runs
+#ifndef FP4_STREAM_SMEM_KB
+#define FP4_STREAM_SMEM_KB 226
+#endif
+constexpr uint32_t kMaxSmem = FP4_STREAM_SMEM_KB * 1024; // per CTA: half an SM, so the next launch (PDL) is resident while this one runs
 constexpr uint32_t kSlot = 4096 + 512;    // one unit: 4 steps x 2 row halves x 32 lanes x 16 B, then 32 lanes x 16 B of absmax
 constexpr uint32_t kMaxRing = 4;
 
@@ -197,7 +206,7 @@ __device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float
 }
 
 // HALF: K % 512 == 256, i.e. the last unit of every row tile holds two steps instead of four
-template <typename T, int NCT, bool HALF>
+template <typename T, int NCT, bool HALF, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(const __grid_constant__ Params p) {
     constexpr int TERMS = sizeof(T) == 4 ? 4 : 2;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -207,9 +216,14 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     const uint32_t K = (uint32_t)p.K, nkb = K >> 6, rowb = K >> 1;  // rowb: packed bytes per weight row
 
     // ---- shared memory carve-up -----------------------------------------------------------------
-    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * p.ring * kSlot + lane * 16;
-    uint8_t* sX = smem + (size_t)kW * p.ring * kSlot;     // [nq][K] s8, pairs of k swapped (nibble order)
-    uint8_t* sZero = sX + (size_t)nq * K;                 // kZeroBytes of zeros
+    // ring_a: where this lane WRITES (and, unless ALIGNED, reads back) its 16 bytes of a 512-byte half step
+    const uint32_t ring_w = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * p.ring * kSlot;
+    const uint32_t ring_a = ring_w + (ALIGNED ? (t * 8 + g) * 16 : lane * 16);
+    const uint32_t ring_am = ring_w + 4096 + lane * 16;   // absmax: lane-private in both variants
+    const uint32_t ring_rd = ring_w + g * 16 + t * 4;     // ALIGNED: word t of chunk i of row g is at + i*128
+    const uint32_t XP = ALIGNED ? K + 16 : K;             // pitch of an x row
+    uint8_t* sX = smem + (size_t)kW * p.ring * kSlot;     // [nq][XP] s8, pairs of k swapped (nibble order)
+    uint8_t* sZero = sX + (size_t)nq * XP;                // kZeroBytes of zeros
     float* sXs = reinterpret_cast<float*>(sZero + kZeroBytes);  // [batch][nkb] 2^-e / 192
     float* sPart = sXs + (size_t)batch * nkb;             // [kW][2][batch*16]
 
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
             }
         }
-        if (2 * (t >> 1) < nst) cp_async_ca16(dst + 4096, ap);  // this lane's 4 blocks exist
+        if (2 * (t >> 1) < nst) cp_async_ca16(dst - ring_a + ring_am, ap);  // this lane's 4 blocks exist
         if (++ld_ku == p.upt) {
             ld_ku = 0;
             loader_at(++ld_gt, 0);  // next row tile (possibly the next matrix of the group)
@@ -325,7 +339,11 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 float y[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) y[i] = f[i] * s;
-                uint8_t* dst = sX + (size_t)(b * TERMS) * K + (size_t)c * 8;
+                // ALIGNED: within a 128-k step the 8-byte chunk (i, t) sits at t*32 + i*8 (a lane's four chunks
+                // are contiguous); otherwise natural order
+                const uint32_t cpos = ALIGNED ? ((uint32_t)c >> 4) * 128 + ((uint32_t)c & 3) * 32 + (((uint32_t)c >> 2) & 3) * 8
+                                              : (uint32_t)c * 8;
+                uint8_t* dst = sX + (size_t)(b * TERMS) * XP + cpos;
 #pragma unroll
                 for (int j = 0; j < TERMS; ++j) {
                     uint32_t ti[8];
@@ -338,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                     // byte order = nibble order of the packed weights: (k+1, k, k+3, k+2)
                     const uint32_t w0 = prmt(prmt(ti[1], ti[0], 0x0040u), prmt(ti[3], ti[2], 0x0040u), 0x5410u);
                     const uint32_t w1 = prmt(prmt(ti[5], ti[4], 0x0040u), prmt(ti[7], ti[6], 0x0040u), 0x5410u);
-                    *reinterpret_cast<uint2*>(dst + (size_t)j * K) = make_uint2(w0, w1);
+                    *reinterpret_cast<uint2*>(dst + (size_t)j * XP) = make_uint2(w0, w1);
                 }
             }
         }
@@ -359,13 +377,23 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     const uint32_t sXs_a = (uint32_t)__cvta_generic_to_shared(sXs);
 #pragma unroll
     for (int ct = 0; ct < NCT; ++ct) {
-        const int col = ct * 8 + (int)g, q = col >> 1, blk = col & 1;
-        const bool valid = q < nq && (int)(t >> 1) == blk;
-        xbase[ct] = valid ? sX_a + (uint32_t)q * K + t * 32 : sZero_a + 16;
-        xstep[ct] = valid ? 512u : 0u;  // bytes per unit
-        int qs = ct * 4 + (int)t;       // the (batch row, term) whose two columns this lane reads back
-        qs = qs < nq ? qs : 0;
-        sbase[ct] = sXs_a + (uint32_t)(qs / TERMS) * nkb * 4;
+        if constexpr (ALIGNED) {
+            const int q = ct * 8 + (int)g;  // MMA column g of tile ct = (batch row, term) q
+            const bool valid = q < nq;
+            xbase[ct] = valid ? sX_a + (uint32_t)q * XP + t * 32 : sZero_a + 16;
+            xstep[ct] = valid ? 512u : 0u;
+            int qs = ct * 8 + 2 * (int)t;   // this lane reads back columns 2t, 2t+1: two terms of one batch row
+            qs = qs < nq ? qs : 0;
+            sbase[ct] = sXs_a + (uint32_t)(qs / TERMS) * nkb * 4;
+        } else {
+            const int col = ct * 8 + (int)g, q = col >> 1, blk = col & 1;
+            const bool valid = q < nq && (int)(t >> 1) == blk;
+            xbase[ct] = valid ? sX_a + (uint32_t)q * K + t * 32 : sZero_a + 16;
+            xstep[ct] = valid ? 512u : 0u;  // bytes per unit
+            int qs = ct * 4 + (int)t;       // the (batch row, term) whose two columns this lane reads back
+            qs = qs < nq ? qs : 0;
+            sbase[ct] = sXs_a + (uint32_t)(qs / TERMS) * nkb * 4;
+        }
     }
     uint32_t tab_lo;
     asm volatile("mov.b32 %0, 0xC0800100;" : "=r"(tab_lo));  // 192*|code[0..3]| = 0, 1, 128, 192
@@ -373,9 +401,13 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     asm volatile("mov.b32 %0, 0x4B400000;" : "=r"(magic_i));
     const uint32_t quad = lane & 28u;
 
-    float acc[NCT][2];  // rows g, g + 8 of (batch row, term) ct*4 + t
+    // !ALIGNED: [0], [1] = rows g, g + 8 of (batch row, term) ct*4 + t.
+    //  ALIGNED: [0], [1] = row g of columns ct*8 + 2t, + 1;  [2], [3] = row g + 8
+    float acc[NCT][ALIGNED ? 4 : 2];
 #pragma unroll
-    for (int ct = 0; ct < NCT; ++ct) acc[ct][0] = acc[ct][1] = 0.f;
+    for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+        for (int i = 0; i < (ALIGNED ? 4 : 2); ++i) acc[ct][i] = 0.f;
 
     float* myPart = sPart + (size_t)warp * 2 * batch * 16;
 
@@ -390,10 +422,28 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         float* part = myPart + (tl == tl_a ? 0 : batch * 16);
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
-            float v0 = acc[ct][0], v1 = acc[ct][1];
-            acc[ct][0] = acc[ct][1] = 0.f;
+            float v0, v1;
             int b;
             bool owner;
+            if constexpr (ALIGNED) {
+                if constexpr (TERMS == 2) {  // the lane holds both terms of batch row ct*4 + t
+                    v0 = fmaf(acc[ct][1], 1.f / 128.f, acc[ct][0]);
+                    v1 = fmaf(acc[ct][3], 1.f / 128.f, acc[ct][2]);
+                    owner = true;
+                    b = ct * 4 + (int)t;
+                } else {  // terms 2(t&1), 2(t&1)+1 of batch row ct*2 + (t>>1); the lane t^1 holds the other two
+                    const float wa = (t & 1) ? (1.f / 16384.f) : 1.f, wb = wa * (1.f / 128.f);
+                    v0 = fmaf(acc[ct][1], wb, acc[ct][0] * wa);
+                    v1 = fmaf(acc[ct][3], wb, acc[ct][2] * wa);
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                    owner = (t & 1) == 0;
+                    b = ct * 2 + (int)(t >> 1);
+                }
+                acc[ct][0] = acc[ct][1] = acc[ct][2] = acc[ct][3] = 0.f;
+            } else {
+            v0 = acc[ct][0]; v1 = acc[ct][1];
+            acc[ct][0] = acc[ct][1] = 0.f;
             if constexpr (TERMS == 2) {
                 const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1), o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
                 v0 = fmaf(o0, 1.f / 128.f, v0);
@@ -410,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
                 owner = t == 0;
                 b = ct;
+            }
             }
             if (owner && b < batch) {
                 if (whole) {
@@ -447,7 +498,8 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         if (left == n) TL_STAMP(4);
 #endif
         const uint32_t sl = ring_a + slot * kSlot;
-        const uint4 amc = lds_u4(sl + 4096);
+        if constexpr (ALIGNED) __syncwarp();  // the lanes read each other's copies
+        const uint4 amc = lds_u4(ring_am + slot * kSlot);
         uint32_t xa[NCT], sa[NCT];
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
@@ -458,6 +510,58 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (HALF && (uint32_t)j >= nst_c) break;
+            if constexpr (ALIGNED) {
+                const uint32_t rd = ring_rd + slot * kSlot + j * 1024;
+                const uint32_t srcA = quad | (2 * (j >> 1)), srcB = srcA + 1;
+                const uint32_t c0 = (j & 1) ? amc.z : amc.x, c1 = (j & 1) ? amc.w : amc.y;
+                const float am[2][2] = {  // [row g / g+8][block 2j / 2j+1]
+                    {__uint_as_float(__shfl_sync(0xffffffffu, c0, srcA)), __uint_as_float(__shfl_sync(0xffffffffu, c1, srcA))},
+                    {__uint_as_float(__shfl_sync(0xffffffffu, c0, srcB)), __uint_as_float(__shfl_sync(0xffffffffu, c1, srcB))}};
+                uint4 bq[NCT][2];
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    bq[ct][0] = lds_u4(xa[ct] + j * 128);
+                    bq[ct][1] = lds_u4(xa[ct] + j * 128 + 16);
+                }
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    int dall[NCT][4], dneg[NCT][4];
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int i = 2 * blk + ii;
+                        const uint32_t wA = gemv::lds_u32(rd + i * 128), wB = gemv::lds_u32(rd + 512 + i * 128);
+                        uint32_t aA0, aA1, nA0, nA1, aB0, aB1, nB0, nB1;
+                        decode_word(wA, tab_lo, aA0, aA1, nA0, nA1);
+                        decode_word(wB, tab_lo, aB0, aB1, nB0, nB1);
+#pragma unroll
+                        for (int ct = 0; ct < NCT; ++ct) {
+                            const uint4 b4 = bq[ct][blk];
+                            const uint2 bx = ii == 0 ? make_uint2(b4.x, b4.y) : make_uint2(b4.z, b4.w);
+                            if (ii == 0) {
+                                imma_first(dall[ct], aA0, aB0, aA1, aB1, bx.x, bx.y, magic_i);
+                                imma_first(dneg[ct], nA0, nB0, nA1, nB1, bx.x, bx.y, magic_i);
+                            } else {
+                                imma_acc(dall[ct], aA0, aB0, aA1, aB1, bx.x, bx.y);
+                                imma_acc(dneg[ct], nA0, nB0, nA1, nB1, bx.x, bx.y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const float xs = __uint_as_float(gemv::lds_u32(sa[ct] + j * 8 + blk * 4));
+                        const float s0 = am[0][blk] * xs, s1 = am[1][blk] * xs;
+                        const float f0 = fmaf(__int_as_float(dneg[ct][0]), -2.f, __int_as_float(dall[ct][0])) + kMagic;
+                        const float f1 = fmaf(__int_as_float(dneg[ct][1]), -2.f, __int_as_float(dall[ct][1])) + kMagic;
+                        const float f2 = fmaf(__int_as_float(dneg[ct][2]), -2.f, __int_as_float(dall[ct][2])) + kMagic;
+                        const float f3 = fmaf(__int_as_float(dneg[ct][3]), -2.f, __int_as_float(dall[ct][3])) + kMagic;
+                        acc[ct][0] = fmaf(f0, s0, acc[ct][0]);
+                        acc[ct][1] = fmaf(f1, s0, acc[ct][1]);
+                        acc[ct][2] = fmaf(f2, s1, acc[ct][2]);
+                        acc[ct][3] = fmaf(f3, s1, acc[ct][3]);
+                    }
+                }
+                continue;
+            }
             const uint4 wA4 = lds_u4(sl + j * 1024), wB4 = lds_u4(sl + j * 1024 + 512);
             const uint32_t wA[4] = {wA4.x, wA4.y, wA4.z, wA4.w};
             const uint32_t wB[4] = {wB4.x, wB4.y, wB4.z, wB4.w};
@@ -474,6 +578,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 bx01 = lds_u4(xa[0] + j * 128);
                 bx23 = lds_u4(xa[0] + j * 128 + 16);
             }
+            // x fragments: 128-bit loads only.  A quarter-warp (lanes g = 2i, 2i+1) reads ONE x row plus the zero
+            // word, so the load is conflict-free; 64-bit loads would put the four rows of a column tile on the
+            // same banks (row pitch K = 0 mod 128): a 4-way conflict that made batch 3..8 shared-memory bound
+            uint4 bq[NCT];
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 uint32_t aA0, aA1, nA0, nA1, aB0, aB1, nB0, nB1;
@@ -482,11 +590,12 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct) {
                     uint2 bx;
-                    if constexpr (NCT == 1) {  // two 128-bit loads per step (conflict-free: a quarter-warp reads one x row)
+                    if constexpr (NCT == 1) {
                         bx = m == 0 ? make_uint2(bx01.x, bx01.y) : m == 1 ? make_uint2(bx01.z, bx01.w)
                            : m == 2 ? make_uint2(bx23.x, bx23.y) : make_uint2(bx23.z, bx23.w);
                     } else {
-                        bx = lds_u2(xa[ct] + j * 128 + m * 8);
+                        if ((m & 1) == 0) bq[ct] = lds_u4(xa[ct] + j * 128 + m * 8);
+                        bx = (m & 1) == 0 ? make_uint2(bq[ct].x, bq[ct].y) : make_uint2(bq[ct].z, bq[ct].w);
                     }
                     if (m == 0) {
                         imma_first(dall[ct], aA0, aB0, aA1, aB1, bx.x, bx.y, magic_i);
@@ -514,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             }
         }
         // every word of the slot has been decoded: refill it with the unit `ring` ahead
+        if constexpr (ALIGNED) __syncwarp();  // ... by every lane
         if (issued < n) issue_unit(sl);
         cp_async_commit();
         slot = slot + 1 == p.ring ? 0 : slot + 1;
@@ -575,8 +685,18 @@ static int env_int(const char* name, int dflt) {
 
 static int nterms(int dtype) { return dtype == FP4_B200_F32 ? 4 : 2; }
 
+// the ALIGNED variant (one MMA column per (batch row, term)): its inner loop is ~45 % slower per column tile
+// (32-bit loads, two-deep IMMA chains, twice the fp32 epilogue), so it pays off where it replaces FOUR column
+// tiles by two - 16-bit inputs with batch 5..8, fp32 with batch 3..4 - and it is what makes fp32 batch 5..8 fit
+// (measured: profiles/r01_gemv_batch_sweep.log)
+static bool use_aligned(int batch, int nt) {
+    static const int enabled = env_int("FP4_B200_GEMV_ALIGNED", 1);  // 0: never, 2: always (experiments)
+    return enabled == 2 || (enabled && batch * nt > 8);
+}
+static int column_tiles(int batch, int nt) { return (batch * nt * (use_aligned(batch, nt) ? 1 : 2) + 7) / 8; }
+
 static size_t fixed_smem_bytes(int batch, int K, int nt) {
-    return (size_t)batch * nt * K + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
+    return (size_t)batch * nt * (K + (use_aligned(batch, nt) ? 16 : 0)) + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
 }
 
 struct Group {
@@ -589,9 +709,9 @@ struct Group {
     int N[kMaxGroup];
 };
 
-template <typename T, int NCT, bool HALF>
+template <typename T, int NCT, bool HALF, bool ALIGNED>
 static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
-    auto kern = gemv_stream_kernel<T, NCT, HALF>;
+    auto kern = gemv_stream_kernel<T, NCT, HALF, ALIGNED>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -657,12 +777,17 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
 
 template <typename T, int NT>
 static int launch_nct(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
-    const int nct = (batch * NT * 2 + 7) / 8;
+    const int nct = column_tiles(batch, NT);
     const bool half = K % 512 != 0;
-#define FP4_GO(NCT) (half ? launch<T, NCT, true>(x, gr, batch, K, st) : launch<T, NCT, false>(x, gr, batch, K, st))
-    if (nct <= 1) return FP4_GO(1);
-    if (nct <= 2) return FP4_GO(2);
-    return FP4_GO(4);
+#define FP4_GO(NCT, AL) (half ? launch<T, NCT, true, AL>(x, gr, batch, K, st) : launch<T, NCT, false, AL>(x, gr, batch, K, st))
+    if (use_aligned(batch, NT)) {
+        if (nct <= 1) return FP4_GO(1, true);
+        if (nct <= 2) return FP4_GO(2, true);
+        return FP4_GO(4, true);
+    }
+    if (nct <= 1) return FP4_GO(1, false);
+    if (nct <= 2) return FP4_GO(2, false);
+    return FP4_GO(4, false);  // only with FP4_B200_GEMV_ALIGNED=0
 #undef FP4_GO
 }
 
@@ -692,7 +817,7 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
     if ((uint64_t)N * (uint64_t)K >= (1ull << 40)) return false;
     if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(absmax) % 16) return false;
     const int nt = nterms(dtype);
-    if ((batch * nt * 2 + 7) / 8 > 4) return false;
+    if (column_tiles(batch, nt) > 4) return false;
     return fixed_smem_bytes(batch, K, nt) + (size_t)kW * kSlot <= kMaxSmem;
 }
 
