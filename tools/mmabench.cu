@@ -36,6 +36,42 @@ __global__ void k(int iters, long long* out, int* sink) {
     if (s + (int)fs == 12345) *sink = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *out = t1 - t0;
 }
+// Does an IMMA overlap with ALU-pipe work of the same sub-partition?  One IMMA + NALU PRMTs per iteration slot:
+// overlapped -> max(8, 2*NALU) cycles, serialised -> 8 + 2*NALU.
+template <int NALU>
+__global__ void mix(int iters, long long* out, int* sink) {
+    int d[8][4];
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) d[i][j] = 0;
+    uint32_t a0 = threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, b0 = a0 * 11, b1 = a0 * 13;
+    uint32_t p[4] = {a0 * 17, a0 * 19, a0 * 23, a0 * 29};
+    __syncthreads();
+    long long t0; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(d[i][0]), "+r"(d[i][1]), "+r"(d[i][2]), "+r"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#pragma unroll
+            for (int q = 0; q < NALU; ++q)  // four independent chains
+                asm volatile("prmt.b32 %0, %0, %1, 0x3120;" : "+r"(p[q & 3]) : "r"(b0));
+        }
+    }
+    __syncthreads(); long long t1; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) :: "memory");
+    int s = p[0] + p[1] + p[2] + p[3];
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += d[i][j];
+    if (s == 12345) *sink = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = t1 - t0;
+}
+template <int NALU>
+static void run_mix(long long* out, int* sink) {
+    const int iters = 2000;
+    for (int warps : {4, 16}) {
+        for (int rep = 0; rep < 2; ++rep) { mix<NALU><<<148, warps * 32>>>(iters, out, sink); cudaDeviceSynchronize(); }
+        long long h; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+        printf("IMMA + %2d PRMT  warps/SM=%2d  %.2f cycles per (IMMA + PRMTs) per sub-partition\n", NALU, warps,
+               (double)h / (iters * 8.0 * (warps / 4)));
+    }
+}
 int main() {
     long long* out; int* sink;
     cudaMalloc(&out, 8); cudaMalloc(&sink, 4);
@@ -56,5 +92,6 @@ int main() {
             printf("%-22s warps/SM=%2d  %.2f cycles per MMA per sub-partition (err=%s)\n", names[kind], warps, per_smsp, cudaGetErrorString(cudaGetLastError()));
         }
     }
+    run_mix<0>(out, sink); run_mix<2>(out, sink); run_mix<4>(out, sink); run_mix<8>(out, sink); run_mix<14>(out, sink);
     return 0;
 }

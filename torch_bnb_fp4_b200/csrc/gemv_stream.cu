@@ -309,11 +309,46 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     {
         const T* x = reinterpret_cast<const T*>(p.x);
         const int nchunk = (int)(K >> 3);
-        for (int b = 0; b < batch; ++b) {
-            for (int c = tid; c < nchunk; c += kThreads) {
-                float f[8];
-                if (in_world > 1) {
-                    if constexpr (sizeof(T) == 2) {
+        // one chunk = 8 consecutive elements of batch row b; a 64-block = the chunks of 8 consecutive lanes
+        auto stage_chunk = [&](int b, int c, float (&f)[8]) {
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[i]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            uint32_t E = (__float_as_uint(mx) >> 23) & 0xFFu;
+            E = E < 32u ? 32u : (E > 250u ? 250u : E);
+            const float s = __uint_as_float((259u - E) << 23);  // 2^(5 - e): |x * s| < 64
+            if ((c & 7) == 0) sXs[b * nkb + (c >> 3)] = __uint_as_float((E - 5u) << 23) * (1.f / 192.f);
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = f[i] * s;
+            // ALIGNED: within a 128-k step the 8-byte chunk (i, t) sits at t*32 + i*8 (a lane's four chunks
+            // are contiguous); otherwise natural order
+            const uint32_t cpos = ALIGNED ? ((uint32_t)c >> 4) * 128 + ((uint32_t)c & 3) * 32 + (((uint32_t)c >> 2) & 3) * 8
+                                          : (uint32_t)c * 8;
+            uint8_t* dst = sX + (size_t)(b * TERMS) * XP + cpos;
+#pragma unroll
+            for (int j = 0; j < TERMS; ++j) {
+                uint32_t ti[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float rr = y[i] + kMagic;  // round to nearest integer
+                    ti[i] = __float_as_uint(rr);
+                    if (j + 1 < TERMS) y[i] = (y[i] - (rr - kMagic)) * 128.f;  // exact residual, rescaled
+                }
+                // byte order = nibble order of the packed weights: (k+1, k, k+3, k+2)
+                const uint32_t w0 = prmt(prmt(ti[1], ti[0], 0x0040u), prmt(ti[3], ti[2], 0x0040u), 0x5410u);
+                const uint32_t w1 = prmt(prmt(ti[5], ti[4], 0x0040u), prmt(ti[7], ti[6], 0x0040u), 0x5410u);
+                *reinterpret_cast<uint2*>(dst + (size_t)j * XP) = make_uint2(w0, w1);
+            }
+        };
+        if (in_world > 1) {
+            if constexpr (sizeof(T) == 2) {
+                for (int b = 0; b < batch; ++b) {
+                    for (int c = tid; c < nchunk; c += kThreads) {
+                        float f[8];
                         const size_t off = ((size_t)b * K + (size_t)c * 8) * 4;
                         tp_load8<T>(in_slot + off, in_tag, f, p.tp.err);
                         for (int r = 1; r < in_world; ++r) {  // fixed rank order: every rank computes the same x
@@ -322,41 +357,37 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f[i] += fr[i];
                         }
+                        stage_chunk(b, c, f);
                     }
-                } else {
-                    XLoad<T>::load(x + (size_t)b * K + c * 8, f);
                 }
-                float mx = 0.f;
+            }
+        } else {
+            // x is [batch][K] contiguous: chunk id = b * nchunk + c.  Four loads in flight per thread - one L2
+            // round trip per four chunks instead of one each (8 rows of K = 8192 are 16 chunks per thread)
+            constexpr int U = 4;
+            const int total = batch * nchunk;  // a multiple of 32: the lanes of a warp are in or out together
+            if (total <= kThreads) {           // one chunk per thread (batch 1, K <= 4096): nothing to overlap
+                if (tid < total) {
+                    float f[8];
+                    XLoad<T>::load(x + (size_t)tid * 8, f);
+                    const int b = batch == 1 ? 0 : tid / nchunk;
+                    stage_chunk(b, tid - b * nchunk, f);
+                }
+            } else
+            for (int base = tid; base < total; base += kThreads * U) {
+                float f[U][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[i]));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-                uint32_t E = (__float_as_uint(mx) >> 23) & 0xFFu;
-                E = E < 32u ? 32u : (E > 250u ? 250u : E);
-                const float s = __uint_as_float((259u - E) << 23);  // 2^(5 - e): |x * s| < 64
-                if ((c & 7) == 0) sXs[b * nkb + (c >> 3)] = __uint_as_float((E - 5u) << 23) * (1.f / 192.f);
-                float y[8];
+                for (int u = 0; u < U; ++u) {
+                    const int id = base + u * kThreads;
+                    if (id < total) XLoad<T>::load(x + (size_t)id * 8, f[u]);
+                }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = f[i] * s;
-                // ALIGNED: within a 128-k step the 8-byte chunk (i, t) sits at t*32 + i*8 (a lane's four chunks
-                // are contiguous); otherwise natural order
-                const uint32_t cpos = ALIGNED ? ((uint32_t)c >> 4) * 128 + ((uint32_t)c & 3) * 32 + (((uint32_t)c >> 2) & 3) * 8
-                                              : (uint32_t)c * 8;
-                uint8_t* dst = sX + (size_t)(b * TERMS) * XP + cpos;
-#pragma unroll
-                for (int j = 0; j < TERMS; ++j) {
-                    uint32_t ti[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float rr = y[i] + kMagic;  // round to nearest integer
-                        ti[i] = __float_as_uint(rr);
-                        if (j + 1 < TERMS) y[i] = (y[i] - (rr - kMagic)) * 128.f;  // exact residual, rescaled
+                for (int u = 0; u < U; ++u) {
+                    const int id = base + u * kThreads;
+                    if (id < total) {
+                        const int b = id / nchunk;
+                        stage_chunk(b, id - b * nchunk, f[u]);
                     }
-                    // byte order = nibble order of the packed weights: (k+1, k, k+3, k+2)
-                    const uint32_t w0 = prmt(prmt(ti[1], ti[0], 0x0040u), prmt(ti[3], ti[2], 0x0040u), 0x5410u);
-                    const uint32_t w1 = prmt(prmt(ti[5], ti[4], 0x0040u), prmt(ti[7], ti[6], 0x0040u), 0x5410u);
-                    *reinterpret_cast<uint2*>(dst + (size_t)j * XP) = make_uint2(w0, w1);
                 }
             }
         }
