@@ -80,19 +80,50 @@ def gemv_bytes(N, K, batch=1, act=2):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every 2 ms (the timed
+    region of the default run is ~80 ms, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001 - older binding name
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:  # noqa: BLE001
+            self.how = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -104,18 +135,24 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self._stop.set()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
+        if self.how:
             self.thread.join(timeout=2)
 
     def summary(self):
+        if self.how == "nvml":
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def synth_layer(N, K, dev, gen):
