@@ -141,6 +141,7 @@ class QuantData:
             self.absmax = state.absmax.float().contiguous()
         self.bias = original_lin.bias if hasattr(original_lin, "bias") else bias
         self._bias_by_dtype = {}
+        self._fast = None
         self.o_type = None
         self.qtype = None
         self.compute_dtype_set = False
@@ -169,6 +170,15 @@ class QuantData:
         else:
             self._bias_t = None
         self.compute_dtype_set = True
+        # pre-validated launcher for the decode GEMV of this dtype (None: take the checked path)
+        self._fast = None
+        if self.nested is None and self.absmax is not None and self.blocksize % 32 == 0 and self.N % 32 == 0:
+            try:
+                self._fast = _ext.GemvLauncher(self.A, self.absmax, self.code, self.blocksize, self.qtype,
+                                               self._Bshape, self._bias_t)
+                self._fast_idx = self.A.device.index
+            except Exception:  # noqa: BLE001 - anything unusual: the checked path reports it properly
+                self._fast = None
 
     # -- dequant ----------------------------------------------------------------------------------
     def _dequantize_codebook(self) -> torch.Tensor:
@@ -218,6 +228,10 @@ class QuantData:
         if A.dtype != self.o_type:
             self.set_compute_type(A)
         rows = n_el // k
+        # decode fast path: 1-2 rows always fit the GEMV; everything validated once in set_compute_type
+        if (rows <= 2 and self._fast is not None and k == self.N and A.is_cuda and A.is_contiguous()
+                and A.device.index == self._fast_idx and torch.cuda.current_device() == self._fast_idx):
+            return self._fast(A, rows)
         gemm_ok = (self.nested is None and self._code_is_std
                    and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype))
         if rows <= GEMV_MAX_BATCH and k % 32 == 0 and self.blocksize % 32 == 0:

@@ -243,6 +243,56 @@ def _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags,
     return out
 
 
+class GemvLauncher:
+    """Pre-validated launcher for ONE layer's decode GEMV (the module's hot path): the checks of `_gemv` are
+    done once here, the per-call work is one torch.empty, one raw-stream query and one ctypes call.  The
+    launcher keeps the tensors alive, so the cached device pointers stay valid; anything it was not built
+    for (another device current, non-contiguous input, another dtype) is the caller's slow path."""
+    __slots__ = ("keep", "pB", "pabs", "pcode", "pbias", "n_out", "k", "blocksize", "dt", "dtcode", "flags",
+                 "dev", "idx", "ws_need", "what")
+
+    def __init__(self, B, absmax, datatype, blocksize, dtype, Bshape, bias):
+        _check_in(B, "B", torch.uint8)
+        _check_in(absmax, "absmax", torch.float32)
+        self.dt = get_scalar_type(dtype)
+        self.n_out, self.k = int(Bshape[0]), int(Bshape[1])
+        if B.numel() * 2 < self.n_out * self.k:
+            raise RuntimeError("B holds fewer than N*K/2 bytes")
+        self.flags = 0
+        self.pcode = None
+        if datatype is not None:
+            _check_in(datatype, "datatype", torch.float32)
+            self.pcode = datatype.data_ptr()
+            if code_is_bnb_fp4(datatype):
+                self.flags |= _lib.FLAG_CODE_IS_BNB_FP4
+        self.pbias = None
+        if bias is not None:
+            _check_in(bias, "bias", self.dt)
+            if bias.numel() != self.n_out:
+                raise RuntimeError("bias must have N entries")
+            self.pbias = bias.data_ptr()
+        self.keep = (B, absmax, datatype, bias)
+        self.pB, self.pabs = B.data_ptr(), absmax.data_ptr()
+        self.blocksize, self.dtcode = int(blocksize), _CODE_OF[self.dt]
+        self.dev, self.idx = B.device, B.device.index
+        self.ws_need = lib.fp4_b200_gemv_workspace_bytes(self.n_out)
+        self.what = "gemv_fp4_bias"
+
+    def __call__(self, A: torch.Tensor, batch: int) -> torch.Tensor:
+        """A: contiguous CUDA tensor [..., K] of the launcher's dtype on the launcher's (current) device."""
+        out = torch.empty(A.shape[:-1] + (self.n_out,), dtype=self.dt, device=self.dev)
+        st = torch._C._cuda_getCurrentRawStream(self.idx)
+        ws = _workspaces.get((self.idx, st))
+        if ws is None or ws.numel() < self.ws_need:
+            ws = _gemv_workspace(self.dev, st, self.n_out)
+        rc = lib.fp4_b200_gemv(A.data_ptr(), self.pB, self.pabs, None, self.pcode, self.pbias, out.data_ptr(),
+                               batch, self.n_out, self.k, self.blocksize, self.dtcode, self.flags,
+                               ws.data_ptr(), ws.numel(), st)
+        if rc:
+            check(rc, self.what)
+        return out
+
+
 def gemv_fp4(A: torch.Tensor, B: torch.Tensor, absmax: torch.Tensor, datatype: torch.Tensor,
              blocksize: int, dtype, Bshape: Sequence[int]) -> torch.Tensor:
     """reference csrc/torch_fp4.cpp:105-123 -> csrc/gemv_fp4_optimized.cu:277-368.
