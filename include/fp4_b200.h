@@ -149,6 +149,20 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                   void* workspace, size_t workspace_bytes, void* stream);
 size_t fp4_b200_gemv_workspace_bytes(int N);
 
+/* Prepared layer: the per-layer constants of fp4_b200_gemv bound once, so that a decode step costs the host
+ * one short call per layer (FFI argument marshalling is a measurable part of an eager, un-graphed token:
+ * the reference pays it per nn.Linear in torch_bnb_fp4/__init__.py:471-492 -> csrc/torch_fp4.cpp:105-123).
+ * The handle is host memory holding the pointers and sizes given here; it does not own or copy the device
+ * buffers, which must outlive it.  fp4_b200_layer_gemv(h, ...) == fp4_b200_gemv(x, packed, absmax, NULL,
+ * code, bias, out, batch, N, K, blocksize, dtype, flags, workspace, workspace_bytes, stream). */
+typedef struct fp4_b200_layer fp4_b200_layer_t;
+fp4_b200_layer_t* fp4_b200_layer_create(const uint8_t* packed, const float* absmax, const float* code,
+                                        const void* bias, int N, int K, int blocksize, int dtype,
+                                        unsigned flags);
+int fp4_b200_layer_gemv(const fp4_b200_layer_t* layer, const void* x, void* out, int batch,
+                        void* workspace, size_t workspace_bytes, void* stream);
+void fp4_b200_layer_destroy(fp4_b200_layer_t* layer);
+
 /* Grouped fused dequant + GEMV: nmat (1..4) weight matrices with the same K applied to the SAME x in one
  * launch - out[m][b, r] = T( sum_k x[b,k] * W_m[r,k] + bias_m[r] ) - e.g. the q/k/v or gate/up projections
  * of a decoder layer, which the reference issues as separate gemv_fp4 calls

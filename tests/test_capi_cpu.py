@@ -66,3 +66,17 @@ def test_tp_struct_layout_matches_header(tmp_path):
     want = [ctypes.sizeof(T), T.in_base.offset, T.slot_bytes.offset, T.out_world.offset, T.out_peer_base.offset,
             T.epochs.offset, T.err.offset, ctypes.sizeof(_lib.Nested)]
     assert got == want
+
+
+def test_prepared_layer_handle_rejects_null_and_destroy_is_null_safe():
+    """fp4_b200_layer_create validates on the host (no GPU needed); a NULL handle is an error, not a crash."""
+    from torch_bnb_fp4_b200 import _lib
+    lib = _lib.lib
+    assert not lib.fp4_b200_layer_create(None, None, None, None, 16, 64, 64, 2, 0)
+    assert not lib.fp4_b200_layer_create(4096, 8192, None, None, 0, 64, 64, 2, 0)
+    h = lib.fp4_b200_layer_create(4096, 8192, None, None, 16, 64, 64, 2, 0)   # pointers are not dereferenced
+    assert h
+    lib.fp4_b200_layer_destroy(h)
+    lib.fp4_b200_layer_destroy(None)
+    assert lib.fp4_b200_layer_gemv(None, None, None, 1, None, 0, None) == -1   # FP4_B200_ERR_NULL
+

@@ -239,6 +239,25 @@ def test_group_projections_inside_an_unmodified_block(cuda):
     assert blk(xl).shape == (2, 30, 512)                  # prefill-sized input: per-layer paths
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prepared_layer_launcher_equals_the_checked_op(cuda, dtype):
+    """fp4_b200_layer_* (the handle the module's decode fast path uses) == fp4_b200_gemv, bit for bit."""
+    N, K = 1024, 1024
+    packed, absmax, _ = synth_quant(N * K, 64, seed=11)
+    g = torch.Generator().manual_seed(12)
+    B, am = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda)
+    code = to_dev(oracle.bnb_code(), cuda)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dtype).to(cuda)
+    launch = ext.GemvLauncher(B, am, code, 64, ST[dtype], [N, K], bias)
+    for shape in [(1, K), (1, 1, K), (2, K)]:
+        x = torch.randn(*shape, generator=g).to(dtype).to(cuda)
+        y = launch(x, x.numel() // K)
+        ref = ext.gemv_fp4_bias(x, B, am, code, 64, ST[dtype], [N, K], bias)
+        assert y.shape == ref.shape == shape[:-1] + (N,)
+        assert torch.equal(y, ref)
+    del launch  # destroys the handle
+
+
 def test_gemv_custom_code_is_honoured(cuda):
     code = np.random.default_rng(3).uniform(-1, 1, 16).astype(np.float32)
     y, exact, _ = _gemv_case(cuda, torch.float32, 128, 512, 2, seed=4, code=code)

@@ -19,7 +19,7 @@ EXPORTS = [
     "fp4_b200_abi_version", "fp4_b200_status_string", "fp4_b200_dequantize",
     "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
     "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
-    "fp4_b200_quantize",
+    "fp4_b200_quantize", "fp4_b200_layer_create", "fp4_b200_layer_gemv", "fp4_b200_layer_destroy",
 ]
 
 
@@ -53,6 +53,9 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_gemv.argtypes = [vp, vp, vp, ctypes.POINTER(Nested), vp, vp, vp, i32, i32, i32,
                                   i32, i32, u32, vp, ctypes.c_size_t, vp]
     lib.fp4_b200_gemv_workspace_bytes.argtypes = [i32]
+    lib.fp4_b200_layer_create.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, u32]
+    lib.fp4_b200_layer_gemv.argtypes = [vp, vp, vp, i32, vp, ctypes.c_size_t, vp]
+    lib.fp4_b200_layer_destroy.argtypes = [vp]
     lib.fp4_b200_gemv_grouped.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                           ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32, vp]
     lib.fp4_b200_gemv_grouped_tp.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
@@ -63,9 +66,12 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the ABI is incomplete
-        if name not in ("fp4_b200_status_string", "fp4_b200_gemv_workspace_bytes"):
+        if name not in ("fp4_b200_status_string", "fp4_b200_gemv_workspace_bytes", "fp4_b200_layer_create",
+                        "fp4_b200_layer_destroy"):
             getattr(lib, name).restype = i32
     lib.fp4_b200_gemv_workspace_bytes.restype = ctypes.c_size_t
+    lib.fp4_b200_layer_create.restype = vp
+    lib.fp4_b200_layer_destroy.restype = None
     if lib.fp4_b200_abi_version() != 1:
         raise ImportError("libfp4_b200.so ABI version mismatch")
     return lib

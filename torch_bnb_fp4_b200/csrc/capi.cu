@@ -1,5 +1,7 @@
 // extern "C" surface of libfp4_b200.so (declared in include/fp4_b200.h): argument validation and
 // kernel selection only; the kernels live in dequant.cu, gemv_generic.cu, gemv_imma.cu, gemm_tcgen05.cu.
+#include <new>
+
 #include "common.cuh"
 
 namespace fp4b200 {
@@ -165,6 +167,32 @@ int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed,
 }
 
 size_t fp4_b200_gemv_workspace_bytes(int N) { return N > 0 ? gemv_imma_workspace_bytes(N) : 0; }
+
+struct fp4_b200_layer {
+    const uint8_t* packed;
+    const float* absmax;
+    const float* code;
+    const void* bias;
+    int N, K, blocksize, dtype;
+    unsigned flags;
+};
+
+fp4_b200_layer_t* fp4_b200_layer_create(const uint8_t* packed, const float* absmax, const float* code,
+                                        const void* bias, int N, int K, int blocksize, int dtype,
+                                        unsigned flags) {
+    if (!packed || !absmax || N <= 0 || K <= 0 || blocksize <= 0) return nullptr;
+    fp4_b200_layer* l = new (std::nothrow) fp4_b200_layer{packed, absmax, code, bias, N, K, blocksize, dtype, flags};
+    return l;
+}
+
+int fp4_b200_layer_gemv(const fp4_b200_layer_t* l, const void* x, void* out, int batch, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!l) return FP4_B200_ERR_NULL;
+    return fp4_b200_gemv(x, l->packed, l->absmax, nullptr, l->code, l->bias, out, batch, l->N, l->K,
+                         l->blocksize, l->dtype, l->flags, workspace, workspace_bytes, stream);
+}
+
+void fp4_b200_layer_destroy(fp4_b200_layer_t* l) { delete l; }
 
 int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, const float* code,
                   const void* bias, void* out, int M, int N, int K, int blocksize, int dtype,

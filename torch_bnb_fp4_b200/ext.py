@@ -248,8 +248,7 @@ class GemvLauncher:
     done once here, the per-call work is one torch.empty, one raw-stream query and one ctypes call.  The
     launcher keeps the tensors alive, so the cached device pointers stay valid; anything it was not built
     for (another device current, non-contiguous input, another dtype) is the caller's slow path."""
-    __slots__ = ("keep", "pB", "pabs", "pcode", "pbias", "n_out", "k", "blocksize", "dt", "dtcode", "flags",
-                 "dev", "idx", "ws_need", "what")
+    __slots__ = ("keep", "handle", "n_out", "k", "dt", "dev", "idx", "ws_need", "what", "_shapes")
 
     def __init__(self, B, absmax, datatype, blocksize, dtype, Bshape, bias):
         _check_in(B, "B", torch.uint8)
@@ -258,36 +257,46 @@ class GemvLauncher:
         self.n_out, self.k = int(Bshape[0]), int(Bshape[1])
         if B.numel() * 2 < self.n_out * self.k:
             raise RuntimeError("B holds fewer than N*K/2 bytes")
-        self.flags = 0
-        self.pcode = None
+        flags = 0
+        pcode = None
         if datatype is not None:
             _check_in(datatype, "datatype", torch.float32)
-            self.pcode = datatype.data_ptr()
+            pcode = datatype.data_ptr()
             if code_is_bnb_fp4(datatype):
-                self.flags |= _lib.FLAG_CODE_IS_BNB_FP4
-        self.pbias = None
+                flags |= _lib.FLAG_CODE_IS_BNB_FP4
+        pbias = None
         if bias is not None:
             _check_in(bias, "bias", self.dt)
             if bias.numel() != self.n_out:
                 raise RuntimeError("bias must have N entries")
-            self.pbias = bias.data_ptr()
+            pbias = bias.data_ptr()
         self.keep = (B, absmax, datatype, bias)
-        self.pB, self.pabs = B.data_ptr(), absmax.data_ptr()
-        self.blocksize, self.dtcode = int(blocksize), _CODE_OF[self.dt]
+        # the constants live in a prepared-layer handle of the C-ABI: 7 marshalled arguments per call, not 16
+        self.handle = lib.fp4_b200_layer_create(B.data_ptr(), absmax.data_ptr(), pcode, pbias, self.n_out, self.k,
+                                                int(blocksize), _CODE_OF[self.dt], flags)
+        if not self.handle:
+            raise RuntimeError("fp4_b200_layer_create failed")
         self.dev, self.idx = B.device, B.device.index
         self.ws_need = lib.fp4_b200_gemv_workspace_bytes(self.n_out)
         self.what = "gemv_fp4_bias"
+        self._shapes = {}
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and lib is not None:
+            lib.fp4_b200_layer_destroy(h)
 
     def __call__(self, A: torch.Tensor, batch: int) -> torch.Tensor:
         """A: contiguous CUDA tensor [..., K] of the launcher's dtype on the launcher's (current) device."""
-        out = torch.empty(A.shape[:-1] + (self.n_out,), dtype=self.dt, device=self.dev)
+        shp = self._shapes.get(A.shape)
+        if shp is None:
+            shp = self._shapes[A.shape] = tuple(A.shape[:-1]) + (self.n_out,)
+        out = torch.empty(shp, dtype=self.dt, device=self.dev)
         st = torch._C._cuda_getCurrentRawStream(self.idx)
         ws = _workspaces.get((self.idx, st))
         if ws is None or ws.numel() < self.ws_need:
             ws = _gemv_workspace(self.dev, st, self.n_out)
-        rc = lib.fp4_b200_gemv(A.data_ptr(), self.pB, self.pabs, None, self.pcode, self.pbias, out.data_ptr(),
-                               batch, self.n_out, self.k, self.blocksize, self.dtcode, self.flags,
-                               ws.data_ptr(), ws.numel(), st)
+        rc = lib.fp4_b200_layer_gemv(self.handle, A.data_ptr(), out.data_ptr(), batch, ws.data_ptr(), ws.numel(), st)
         if rc:
             check(rc, self.what)
         return out
