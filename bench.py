@@ -80,17 +80,18 @@ def gemv_bytes(N, K, batch=1, act=2):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every 2 ms (the timed
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every 4 ms (the timed
     region of the default run is ~80 ms, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, enabled=True):
         self.rows, self.proc, self.index = [], None, index
         self.sm, self.mx, self.reasons, self.how = [], [], set(), None
         self._stop = threading.Event()
+        self.enabled = enabled  # only the rank that prints samples: eight processes polling the driver perturb it
 
     def _nvml_loop(self, nv, h):
         while not self._stop.is_set():
@@ -105,9 +106,11 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -146,7 +149,7 @@ class ClockSampler:
         if self.how == "nvml":
             sm = sorted(self.sm)
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 4 ms period"}
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -381,7 +384,7 @@ def run_ours(args, rank, world):
     for _ in range(args.warmup):
         runner.graph.replay()
     barrier()
-    with ClockSampler(dev.index) as clk:
+    with ClockSampler(dev.index, enabled=(rank == 0)) as clk:
         t_dev = time_events(runner.graph.replay, args.steps)
     barrier()
     t_dev = maxrank(t_dev)
