@@ -219,6 +219,14 @@ class QuantData:
                              self._bias_t)
 
     def forward(self, A: torch.Tensor) -> torch.Tensor:
+        # decode fast path first (1-2 rows always fit the GEMV; everything else was validated once in
+        # set_compute_type): as few interpreter steps as possible between the module call and the launch
+        f = self._fast
+        if f is not None and A.dtype is self.o_type and A.shape[-1] == self.N:
+            n_el = A.numel()
+            if ((n_el == self.N or n_el == 2 * self.N) and A.is_contiguous()
+                    and A.device.index == self._fast_idx == torch.cuda.current_device()):
+                return f(A, 1 if n_el == self.N else 2)
         k = A.shape[-1]
         n_el = A.numel()
         if n_el == 0:  # same shapes as the reference's empty-input branch (:580-589)
@@ -228,10 +236,6 @@ class QuantData:
         if A.dtype != self.o_type:
             self.set_compute_type(A)
         rows = n_el // k
-        # decode fast path: 1-2 rows always fit the GEMV; everything validated once in set_compute_type
-        if (rows <= 2 and self._fast is not None and k == self.N and A.is_cuda and A.is_contiguous()
-                and A.device.index == self._fast_idx and torch.cuda.current_device() == self._fast_idx):
-            return self._fast(A, rows)
         gemm_ok = (self.nested is None and self._code_is_std
                    and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype))
         if rows <= GEMV_MAX_BATCH and k % 32 == 0 and self.blocksize % 32 == 0:
