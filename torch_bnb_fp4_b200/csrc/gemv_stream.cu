@@ -91,6 +91,7 @@ struct Params {
     uint32_t upt;     // units per row tile = ceil(K / 512)
     uint32_t tq, tr;  // CTA c owns tiles [c*tq + min(c,tr), +tq + (c<tr))
     uint32_t ring;    // unit slots per warp (1..kMaxRing)
+    uint32_t pre;     // steps (1..4) of the first slot issued before griddepcontrol.wait
     FastDiv by_upt;
     fp4_b200_tp_t tp;  // tensor-parallel exchange through peer memory (in_world / out_world <= 1: off)
     long long* tl;    // debug timeline (FP4_STREAM_TIMELINE builds): [cta][warp][8] globaltimer ns
@@ -257,16 +258,18 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     TL_STAMP(0);
     uint32_t ld_ku = ku_a, issued = 0;
     // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
-    auto issue_unit = [&](uint32_t dst) {
+    // (steps [j0, j1) of the unit; the absmax rides with step 0, the loader advances after step 3)
+    auto issue_steps = [&](uint32_t dst, uint32_t j0, uint32_t j1) {
         const uint32_t nst = (HALF && ld_ku + 1 == p.upt) ? 2u : 4u;  // a tile's last unit may be half a unit
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if ((uint32_t)j < nst) {
+            if ((uint32_t)j >= j0 && (uint32_t)j < j1 && (uint32_t)j < nst) {
                 cp_async_cg16(dst + j * 1024, wp + j * 64);
                 cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
             }
         }
-        if (2 * (t >> 1) < nst) cp_async_ca16(dst - ring_a + ring_am, ap);  // this lane's 4 blocks exist
+        if (j0 == 0 && 2 * (t >> 1) < nst) cp_async_ca16(dst - ring_a + ring_am, ap);  // this lane's 4 blocks exist
+        if (j1 < 4) return;
         if (++ld_ku == p.upt) {
             ld_ku = 0;
             loader_at(++ld_gt, 0);  // next row tile (possibly the next matrix of the group)
@@ -276,11 +279,14 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         }
         ++issued;
     };
+    auto issue_unit = [&](uint32_t dst) { issue_steps(dst, 0, 4); };
     // ---- 1. fill the ring: nothing here depends on the previous kernel in the stream ----------------
     // (only the first slot here: issuing a deep ring costs microseconds of LSU time that would delay the
     // x staging everything else waits for; the other slots are filled right after it)
-    if (issued < n) issue_unit(ring_a);
-    cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
+    // p.pre steps of the first slot go out here; the rest of it follows the x loads (same cp.async group)
+    const bool have0 = issued < n;
+    if (have0) issue_steps(ring_a, 0, p.pre);
+    if (p.pre >= 4) cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
     TL_STAMP(1);
     // x and `out` may be products of the previous kernel: wait for it, then let the next kernel start
     // its own prologue (its prefetches run while this kernel computes)
@@ -316,6 +322,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         auto fill_ring = [&]() {
             if (ring_filled) return;
             ring_filled = true;
+            if (p.pre < 4) {
+                if (have0) issue_steps(ring_a, p.pre, 4);
+                cp_async_commit();
+            }
             for (uint32_t r = 1; r < p.ring; ++r) {
                 if (issued < n) issue_unit(ring_a + r * kSlot);
                 cp_async_commit();
@@ -798,6 +808,8 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     if (ring > kMaxRing) ring = kMaxRing;
     if (ring < 1) ring = 1;
     p.ring = ring;
+    static const int pre_steps = env_int("FP4_B200_GEMV_PRE_STEPS", 4);
+    p.pre = (uint32_t)(pre_steps < 1 ? 1 : pre_steps > 4 ? 4 : pre_steps);
     p.tl = nullptr;
 #ifdef FP4_STREAM_TIMELINE
     if (g_stream_tl) p.tl = g_stream_tl + (size_t)(g_stream_tl_launch++) * (kNumSMs * kW * 8);
