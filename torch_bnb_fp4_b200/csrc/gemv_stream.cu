@@ -808,8 +808,12 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     if (ring > kMaxRing) ring = kMaxRing;
     if (ring < 1) ring = 1;
     p.ring = ring;
-    static const int pre_steps = env_int("FP4_B200_GEMV_PRE_STEPS", 4);
-    p.pre = (uint32_t)(pre_steps < 1 ? 1 : pre_steps > 4 ? 4 : pre_steps);
+    // how much of the first slot goes out before griddepcontrol.wait: the x loads queue behind those bytes.
+    // Where x staging is short (one chunk per thread) and every SM streams, half a slot measured 2-3 % faster;
+    // small grids and long K (more chunks of x per thread) want the whole slot
+    static const int pre_steps = env_int("FP4_B200_GEMV_PRE_STEPS", 0);
+    if (pre_steps > 0) p.pre = (uint32_t)(pre_steps > 4 ? 4 : pre_steps);
+    else p.pre = (batch * K <= 4096 && tiles >= (uint32_t)kNumSMs) ? 2u : 4u;
     p.tl = nullptr;
 #ifdef FP4_STREAM_TIMELINE
     if (g_stream_tl) p.tl = g_stream_tl + (size_t)(g_stream_tl_launch++) * (kNumSMs * kW * 8);
