@@ -12,9 +12,11 @@
 // memory, filled with 16-byte cp.async copies laid out directly in MMA-fragment order (lane l's bytes
 // at lane l's slot: each lane reads back only what it copied, so there are no barriers, no bank
 // conflicts and no cross-lane visibility to wait for — cp.async.wait_group is the only
-// synchronisation).  The ring is filled BEFORE griddepcontrol.wait: under programmatic dependent
-// launch the next layer's first units are already on their way while the current layer finishes, and a
-// layer of <= 1 unit per warp (4096x4096) is entirely in flight before its input exists.
+// synchronisation; the ALIGNED variant below adds a __syncwarp).  The first ring slot (or half of it, see
+// p.pre) is issued BEFORE griddepcontrol.wait: under programmatic dependent launch the next layer's first
+// units are already on their way while the current layer finishes, and a layer of <= 1 unit per warp
+// (4096x4096) is entirely in flight before its input exists.  The rest of the ring goes out between the loads
+// of x and their first use, so its LSU time overlaps the L2 round trip of x.
 //
 // Arithmetic side (must stay under ~20 issue slots per 8 weights to keep up with HBM):
 //   * weights: 192*|code| = {0,1,128,192,64,96,32,48} fits a byte: one PRMT against that 8-entry table
