@@ -338,6 +338,7 @@ class TorchFP4LinearGroup(nn.Module):
         qds = [m.quant_data for m in self.layers]
         self._groupable = (len(qds) <= 4 and all(q.nested is None and q._code_is_std and q.blocksize == 64
                                                  for q in qds) and len({q.N for q in qds}) == 1)
+        self._launchers = {}
 
     def forward(self, x: torch.Tensor):
         qds = [m.quant_data for m in self.layers]
@@ -347,6 +348,20 @@ class TorchFP4LinearGroup(nn.Module):
             for q in qds:
                 if x.dtype != q.o_type:
                     q.set_compute_type(x)
+            # pre-validated launcher per input dtype (pointer arrays built once)
+            if x.is_cuda and x.is_contiguous() and x.device.index == torch.cuda.current_device():
+                la = self._launchers.get(x.dtype)
+                if la is None:
+                    try:
+                        la = _ext.GroupLauncher([q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
+                                                [q._Bshape for q in qds], [q._bias_t for q in qds])
+                    except Exception:  # noqa: BLE001 - the checked path below reports it properly
+                        la = False
+                    self._launchers[x.dtype] = la
+                if la and la.idx == x.device.index:
+                    outs = la(x, rows)
+                    if outs is not None:
+                        return tuple(outs)
             xc = x if x.is_contiguous() else x.contiguous()
             outs = _ext.gemv_fp4_grouped(xc, [q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
                                          [q._Bshape for q in qds], [q._bias_t for q in qds])

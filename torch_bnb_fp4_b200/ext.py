@@ -378,6 +378,59 @@ def gemv_fp4_grouped(A: Optional[torch.Tensor], Bs: Sequence[torch.Tensor], absm
     return list(outs)
 
 
+class GroupLauncher:
+    """Pre-validated launcher for a group of layers that share the input (see GemvLauncher): the pointer
+    arrays of fp4_b200_gemv_grouped are built once, a call allocates the outputs and fills in their pointers."""
+    __slots__ = ("keep", "n", "pk", "am", "bi", "ou", "ns", "n_outs", "k", "blocksize", "dt", "dtcode", "dev",
+                 "idx", "unsupported")
+
+    def __init__(self, Bs, absmaxes, blocksize, dtype, Bshapes, biases=None):
+        self.dt = get_scalar_type(dtype)
+        n = self.n = len(Bs)
+        if n < 1 or n > 4 or len(absmaxes) != n or len(Bshapes) != n:
+            raise RuntimeError("a group holds 1..4 layers")
+        self.k = int(Bshapes[0][1])
+        if any(int(sh[1]) != self.k for sh in Bshapes):
+            raise RuntimeError("grouped GEMV: every weight must have the same in_features")
+        for B, a in zip(Bs, absmaxes):
+            _check_in(B, "B", torch.uint8)
+            _check_in(a, "absmax", torch.float32)
+        vp = ctypes.c_void_p
+        self.n_outs = [int(sh[0]) for sh in Bshapes]
+        self.pk = (vp * n)(*[B.data_ptr() for B in Bs])
+        self.am = (vp * n)(*[a.data_ptr() for a in absmaxes])
+        self.ou = (vp * n)()
+        self.ns = (ctypes.c_int * n)(*self.n_outs)
+        self.bi = None
+        if biases is not None and any(b is not None for b in biases):
+            for b in biases:
+                if b is not None:
+                    _check_in(b, "bias", self.dt)
+            self.bi = (vp * n)(*[None if b is None else b.data_ptr() for b in biases])
+        self.keep = (list(Bs), list(absmaxes), None if biases is None else list(biases))
+        self.blocksize, self.dtcode = int(blocksize), _CODE_OF[self.dt]
+        self.dev, self.idx = Bs[0].device, Bs[0].device.index
+        self.unsupported = set()  # batch sizes the grouped kernel refused (FP4_B200_ERR_UNSUPPORTED)
+
+    def __call__(self, A: torch.Tensor, batch: int):
+        """A: contiguous [..., K] of the launcher's dtype on the launcher's (current) device; None = unsupported."""
+        if batch in self.unsupported:
+            return None
+        lead = tuple(A.shape[:-1])
+        outs = [torch.empty(lead + (m,), dtype=self.dt, device=self.dev) for m in self.n_outs]
+        for i, o in enumerate(outs):
+            self.ou[i] = o.data_ptr()
+        st = torch._C._cuda_getCurrentRawStream(self.idx)
+        rc = lib.fp4_b200_gemv_grouped(A.data_ptr(), self.n, self.pk, self.am, self.bi, self.ou, self.ns, batch,
+                                       self.k, self.blocksize, self.dtcode, _lib.FLAG_CODE_IS_BNB_FP4, st)
+        if rc == -7:
+            self.unsupported.add(batch)
+            return None
+        if rc:
+            check(rc, "gemv_fp4_grouped")
+        return outs
+
+
 def gemm_fp4(A_in: torch.Tensor, A: torch.Tensor, absmax: torch.Tensor,
              codebook: Optional[torch.Tensor], M: int, N: int, blocksize: int,
              bias: Optional[torch.Tensor] = None) -> torch.Tensor:
