@@ -397,8 +397,47 @@ def run_ours(args, rank, world):
             runner_g.graph.replay()
         barrier()
         t_grp = maxrank(time_events(runner_g.graph.replay, args.steps))
+        # the same through group_projections(): the UNMODIFIED per-projection step function, q/k/v and gate/up
+        # sharing launches behind the modules' backs
+        import torch_bnb_fp4
+
+        class _Block(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.q_proj, self.k_proj, self.v_proj, self.o_proj = m["q"], m["k"], m["v"], m["o"]
+                self.gate_proj, self.up_proj, self.down_proj = m["gate"], m["up"], m["down"]
+
+        blocks = [_Block(m) for m in layers]
+        n_groups = sum(torch_bnb_fp4.group_projections(b) for b in blocks)
+
+        def step_dropin(h):
+            for b in blocks:
+                q = b.q_proj(h)
+                b.k_proj(h)
+                b.v_proj(h)
+                o = b.o_proj(q)
+                b.gate_proj(o)
+                up = b.up_proj(o)
+                h = b.down_proj(up)
+            return h
+
+        runner_d = GraphedCallable(step_dropin, [h0], warmup=3)
+        for _ in range(args.warmup):
+            runner_d.graph.replay()
+        t_drop = time_events(runner_d.graph.replay, args.steps)
+        with torch.no_grad():
+            for _ in range(2):
+                step_dropin(h0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                step_dropin(h0)
+            torch.cuda.synchronize()
+            t_drop_eager = (time.perf_counter() - t0) / 10
+        dropin = {"groups": n_groups, "tok_per_s": args.steps / t_drop, "eager_tok_per_s": 1.0 / t_drop_eager,
+                  "what": "group_projections(block) on blocks whose forward calls q/k/v/o/gate/up/down one by one"}
     else:
-        t_grp = None
+        t_grp, dropin = None, None
 
     # end to end: pinned host input -> H2D -> replay -> D2H of the result, every step
     def e2e_step():
@@ -461,7 +500,8 @@ def run_ours(args, rank, world):
                              "ms_per_step": t_grp / args.steps * 1e3, "launches_per_step": len(layers) * 4,
                              "frac_of_peak": nbytes * args.steps / t_grp / 1e9 / world / peak,
                              "what": "extension: q/k/v and gate/up each issued as one fp4_b200_gemv_grouped launch "
-                                     "(TorchFP4LinearGroup); same arithmetic up to fp32 summation order, 4 instead of 7 launches per layer"},
+                                     "(TorchFP4LinearGroup); same arithmetic up to fp32 summation order, 4 instead of 7 launches per layer",
+                             "dropin": dropin},
     }
     if nccl_line is not None:
         nccl_line["value"] = nbytes / (nccl_line["ms_per_step"] * 1e-3) / 1e9
