@@ -282,9 +282,12 @@ class GemvLauncher:
         self._shapes = {}
 
     def __del__(self):
-        h, self.handle = getattr(self, "handle", None), None
-        if h and lib is not None:
-            lib.fp4_b200_layer_destroy(h)
+        try:
+            h, self.handle = getattr(self, "handle", None), None
+            if h and lib is not None:
+                lib.fp4_b200_layer_destroy(h)
+        except Exception:  # noqa: BLE001 - interpreter shutdown: the library may already be gone
+            pass
 
     def __call__(self, A: torch.Tensor, batch: int) -> torch.Tensor:
         """A: contiguous CUDA tensor [..., K] of the launcher's dtype on the launcher's (current) device."""
