@@ -163,6 +163,15 @@ int fp4_b200_layer_gemv(const fp4_b200_layer_t* layer, const void* x, void* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 void fp4_b200_layer_destroy(fp4_b200_layer_t* layer);
 
+/* Prepared GROUP of 1..4 layers that share the input (fp4_b200_gemv_grouped with its host arrays bound once).
+ * fp4_b200_layer_gemv_grouped(h, x, out[], batch, tp, stream) == fp4_b200_gemv_grouped_tp(x, nmat, packed, absmax,
+ * bias, out, N, batch, K, blocksize, dtype, flags, tp, stream); `out` is a HOST array of nmat device pointers. */
+fp4_b200_layer_t* fp4_b200_layer_create_grouped(int nmat, const uint8_t* const* packed, const float* const* absmax,
+                                                const float* code, const void* const* bias, const int* N, int K,
+                                                int blocksize, int dtype, unsigned flags);
+int fp4_b200_layer_gemv_grouped(const fp4_b200_layer_t* layer, const void* x, void* const* out, int batch,
+                                const fp4_b200_tp_t* tp, void* stream);
+
 /* Grouped fused dequant + GEMV: nmat (1..4) weight matrices with the same K applied to the SAME x in one
  * launch - out[m][b, r] = T( sum_k x[b,k] * W_m[r,k] + bias_m[r] ) - e.g. the q/k/v or gate/up projections
  * of a decoder layer, which the reference issues as separate gemv_fp4 calls

@@ -102,3 +102,19 @@ def test_bnb_4bit_serialisation_round_trip_cpu():
     back = bc.quant_state_from_dict(d)
     assert back.nested and torch.equal(back.absmax, nested.absmax) and back.state2.blocksize == 256
     assert torch.equal(back.state2.code, state2.code) and abs(float(back.offset) - 0.0371) < 1e-6
+
+
+def test_codebook_identity_accepts_either_sign_of_zero():
+    """bitsandbytes' QuantState.code has +0.0 at index 8 (the Python literal -0 is an int); the reference table has
+    -0.0.  Both must select the fast kernels (a bitwise compare rejected every real bnb layer)."""
+    import torch
+    from torch_bnb_fp4_b200 import ext
+    ref = torch.tensor(ext.BNB_FP4_CODE, dtype=torch.float32)
+    assert ext.code_is_bnb_fp4(ref)
+    plus = ref.clone()
+    plus[8] = 0.0
+    assert not torch.signbit(plus[8]) and ext.code_is_bnb_fp4(plus)
+    other = ref.clone()
+    other[4] = 0.333333  # the reference's CODE_PARAM quirk: a different table, generic kernel
+    assert not ext.code_is_bnb_fp4(other)
+    assert not ext.code_is_bnb_fp4(ref[:8].clone())

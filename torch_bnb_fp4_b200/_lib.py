@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfp4_b200.so")
+# FP4_B200_LIB: a differently built copy of the library (kernel A/B experiments in tools/); default in-tree build
+LIB_PATH = os.environ.get("FP4_B200_LIB") or os.path.join(HERE, "libfp4_b200.so")
 
 F16, F32, BF16 = 0, 1, 2
 FLAG_CODE_IS_BNB_FP4 = 1
@@ -20,6 +21,7 @@ EXPORTS = [
     "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
     "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
     "fp4_b200_quantize", "fp4_b200_layer_create", "fp4_b200_layer_gemv", "fp4_b200_layer_destroy",
+    "fp4_b200_layer_create_grouped", "fp4_b200_layer_gemv_grouped",
 ]
 
 
@@ -56,6 +58,9 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_layer_create.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, u32]
     lib.fp4_b200_layer_gemv.argtypes = [vp, vp, vp, i32, vp, ctypes.c_size_t, vp]
     lib.fp4_b200_layer_destroy.argtypes = [vp]
+    lib.fp4_b200_layer_create_grouped.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, ctypes.POINTER(vp),
+                                                  ctypes.POINTER(i32), i32, i32, i32, u32]
+    lib.fp4_b200_layer_gemv_grouped.argtypes = [vp, vp, ctypes.POINTER(vp), i32, ctypes.POINTER(TpExchange), vp]
     lib.fp4_b200_gemv_grouped.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                           ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32, vp]
     lib.fp4_b200_gemv_grouped_tp.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
@@ -67,10 +72,11 @@ def _load() -> ctypes.CDLL:
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the ABI is incomplete
         if name not in ("fp4_b200_status_string", "fp4_b200_gemv_workspace_bytes", "fp4_b200_layer_create",
-                        "fp4_b200_layer_destroy"):
+                        "fp4_b200_layer_create_grouped", "fp4_b200_layer_destroy"):
             getattr(lib, name).restype = i32
     lib.fp4_b200_gemv_workspace_bytes.restype = ctypes.c_size_t
     lib.fp4_b200_layer_create.restype = vp
+    lib.fp4_b200_layer_create_grouped.restype = vp
     lib.fp4_b200_layer_destroy.restype = None
     if lib.fp4_b200_abi_version() != 1:
         raise ImportError("libfp4_b200.so ABI version mismatch")

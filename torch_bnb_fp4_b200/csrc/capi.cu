@@ -169,27 +169,52 @@ int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed,
 size_t fp4_b200_gemv_workspace_bytes(int N) { return N > 0 ? gemv_imma_workspace_bytes(N) : 0; }
 
 struct fp4_b200_layer {
-    const uint8_t* packed;
-    const float* absmax;
+    int nmat;
+    const uint8_t* packed[4];
+    const float* absmax[4];
+    const void* bias[4];
+    int N[4];
     const float* code;
-    const void* bias;
-    int N, K, blocksize, dtype;
+    int K, blocksize, dtype;
     unsigned flags;
 };
+
+fp4_b200_layer_t* fp4_b200_layer_create_grouped(int nmat, const uint8_t* const* packed, const float* const* absmax,
+                                                const float* code, const void* const* bias, const int* N, int K,
+                                                int blocksize, int dtype, unsigned flags) {
+    if (nmat < 1 || nmat > 4 || !packed || !absmax || !N || K <= 0 || blocksize <= 0) return nullptr;
+    fp4_b200_layer* l = new (std::nothrow) fp4_b200_layer();
+    if (!l) return nullptr;
+    l->nmat = nmat;
+    for (int m = 0; m < nmat; ++m) {
+        if (!packed[m] || !absmax[m] || N[m] <= 0) { delete l; return nullptr; }
+        l->packed[m] = packed[m]; l->absmax[m] = absmax[m]; l->bias[m] = bias ? bias[m] : nullptr; l->N[m] = N[m];
+    }
+    l->code = code; l->K = K; l->blocksize = blocksize; l->dtype = dtype; l->flags = flags;
+    return l;
+}
 
 fp4_b200_layer_t* fp4_b200_layer_create(const uint8_t* packed, const float* absmax, const float* code,
                                         const void* bias, int N, int K, int blocksize, int dtype,
                                         unsigned flags) {
-    if (!packed || !absmax || N <= 0 || K <= 0 || blocksize <= 0) return nullptr;
-    fp4_b200_layer* l = new (std::nothrow) fp4_b200_layer{packed, absmax, code, bias, N, K, blocksize, dtype, flags};
-    return l;
+    return fp4_b200_layer_create_grouped(1, &packed, &absmax, code, &bias, &N, K, blocksize, dtype, flags);
 }
 
-int fp4_b200_layer_gemv(const fp4_b200_layer_t* l, const void* x, void* out, int batch, void* workspace,
+int fp4_b200_layer_gemv(const fp4_b200_layer_t* lc, const void* x, void* out, int batch, void* workspace,
                         size_t workspace_bytes, void* stream) {
-    if (!l) return FP4_B200_ERR_NULL;
-    return fp4_b200_gemv(x, l->packed, l->absmax, nullptr, l->code, l->bias, out, batch, l->N, l->K,
+    if (!lc) return FP4_B200_ERR_NULL;
+    if (lc->nmat != 1) return FP4_B200_ERR_SHAPE;
+    const fp4_b200_layer* l = lc;
+    return fp4_b200_gemv(x, l->packed[0], l->absmax[0], nullptr, l->code, l->bias[0], out, batch, l->N[0], l->K,
                          l->blocksize, l->dtype, l->flags, workspace, workspace_bytes, stream);
+}
+
+int fp4_b200_layer_gemv_grouped(const fp4_b200_layer_t* lc, const void* x, void* const* out, int batch,
+                                const fp4_b200_tp_t* tp, void* stream) {
+    if (!lc || !out) return FP4_B200_ERR_NULL;
+    const fp4_b200_layer* l = lc;
+    return fp4_b200_gemv_grouped_tp(x, l->nmat, l->packed, l->absmax, l->bias, out, l->N, batch, l->K, l->blocksize,
+                                    l->dtype, l->flags, tp, stream);
 }
 
 void fp4_b200_layer_destroy(fp4_b200_layer_t* l) { delete l; }

@@ -116,6 +116,16 @@ static inline size_t fp4b200_ws_counter_bytes(int N) {
     return (((size_t)(N + 15) / 16) * 4 + 255) & ~(size_t)255;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a once-flag per device, not per process
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& flag() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[(d < 0 || d >= 64) ? 0 : d];
+    }
+};
+
 static inline int ilog2_exact(int64_t v) {  // -1 if v is not a power of two
     if (v <= 0 || (v & (v - 1))) return -1;
     int l = 0;

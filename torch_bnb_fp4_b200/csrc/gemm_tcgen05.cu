@@ -761,11 +761,11 @@ static int launch(const void* x, const uint8_t* packed, const float* absmax, con
     if (stagesB > 8) stagesB = 8;
     const size_t smem = (size_t)stagesB * kStageB + kWSlots * kWBox + (kStagesA + stagesB) * 16 + 32 + kWSlots * 16 + 64 + 1024;
     auto kern = gemm_fp4_tcgen05_kernel<T, BT>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.flag() = true;
     }
     Params p;
     p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;

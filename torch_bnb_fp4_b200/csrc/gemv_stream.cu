@@ -189,21 +189,34 @@ __device__ __forceinline__ uint32_t tp_word(float v, uint32_t tag) {
     }
     return (uint32_t)h | (tag << 16);
 }
-// 8 consecutive elements of rank `r`'s partial for the epoch with tag `tag`; waits for late words
+// 8 consecutive elements of rank `r`'s partial for the epoch with tag `tag`; waits for late words.  A peer that
+// has not delivered after kTpTimeoutNs (a dead rank, or call sequences that diverged) is fatal: the flag is
+// raised for the host and the kernel traps instead of computing with unvalidated words.
+constexpr unsigned long long kTpTimeoutNs = 20ull * 1000 * 1000 * 1000;
 template <typename T>
 __device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float (&f)[8], uint32_t* err) {
-    uint32_t spins = 0;
-    for (;;) {
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
         const uint4 a = ld_peer_u4(src), b = ld_peer_u4(src + 16);
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < 8; ++i) ok = ok && (w[i] >> 16) == tag;
-        if (ok || ++spins > (1u << 19)) {  // a peer died or the call sequences diverged: flag it, do not hang
-            if (!ok) *err = 1u;
+        if (ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = tp_word_value<T>(w[i]);
             return;
+        }
+        if ((spins & 4095u) == 4095u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > kTpTimeoutNs) {
+                *reinterpret_cast<volatile uint32_t*>(err) = 1u;
+                __threadfence_system();
+                asm volatile("trap;");
+            }
         }
     }
 }
@@ -258,6 +271,9 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     };
     loader_at(ld_gt, ku_a);
     TL_STAMP(0);
+    // the next kernel of the stream may be scheduled as soon as every CTA of this one is running: its CTAs then
+    // start (and request their first ring slot) the moment a CTA of this kernel leaves its SM
+    asm volatile("griddepcontrol.launch_dependents;");
     uint32_t ld_ku = ku_a, issued = 0;
     // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
     // (steps [j0, j1) of the unit; the absmax rides with step 0, the loader advances after step 3)
@@ -290,10 +306,8 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     if (have0) issue_steps(ring_a, 0, p.pre);
     if (p.pre >= 4) cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
     TL_STAMP(1);
-    // x and `out` may be products of the previous kernel: wait for it, then let the next kernel start
-    // its own prologue (its prefetches run while this kernel computes)
+    // x and `out` may be products of the previous kernel: wait for it
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");
     TL_STAMP(2);
     // tensor parallel (see the helpers above).  Epochs: [0] = last published by this rank's producers,
     // [1] = last finished by its consumers; both only change between the kernels that read them.
@@ -762,17 +776,46 @@ struct Group {
     int N[kMaxGroup];
 };
 
+// how a launch deals the row tiles to CTAs and sizes the per-warp rings
+struct Partition {
+    uint32_t grid, upt, tq, tr, ring;
+};
+static Partition partition(uint32_t tiles, int batch, int K, int nt) {
+    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", FP4_STREAM_MINB);
+    static const int max_ring = env_int("FP4_B200_GEMV_RING", (int)kMaxRing);
+    static const int smem_cap = env_int("FP4_B200_GEMV_SMEM_KB", (int)(kMaxSmem / 1024 / FP4_STREAM_MINB)) * 1024;
+    Partition pt;
+    const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
+    pt.grid = tiles < max_grid ? tiles : max_grid;
+    pt.upt = ((uint32_t)K + 511) / 512;
+    pt.tq = tiles / pt.grid;
+    pt.tr = tiles % pt.grid;
+    // ring depth: no deeper than a warp has units, no larger than shared memory allows
+    const size_t fixed = fixed_smem_bytes(batch, K, nt);
+    const uint32_t units_per_warp = ((pt.tq + (pt.tr ? 1u : 0u)) * pt.upt + kW - 1) / kW;
+    uint32_t ring = (size_t)smem_cap > fixed ? (uint32_t)(((size_t)smem_cap - fixed) / ((size_t)kW * kSlot)) : 1u;
+    if (ring > units_per_warp) ring = units_per_warp;
+    if (ring > (uint32_t)max_ring) ring = (uint32_t)max_ring;
+    if (ring > kMaxRing) ring = kMaxRing;
+    if (ring < 1) ring = 1;
+    pt.ring = ring;
+    return pt;
+}
+
 template <typename T, int NCT, bool HALF, bool ALIGNED>
 static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
     auto kern = gemv_stream_kernel<T, NCT, HALF, ALIGNED>;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to large dynamic shared memory is per device (a process may drive several GPUs)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FP4_B200_ERR_UNSUPPORTED;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev] = true;
     }
     static const int use_pdl = env_int("FP4_B200_GEMV_PDL", 1);
-    static const int max_ring = env_int("FP4_B200_GEMV_RING", (int)kMaxRing);
     Params p;
     p.x = x;
     p.batch = batch; p.K = K;
@@ -794,22 +837,12 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
             p.vpacked[m] = nullptr; p.vabsmax[m] = nullptr; p.vbias[m] = nullptr; p.vout[m] = nullptr; p.Nm[m] = 0;
         }
     }
-    static const int ctas_per_sm = env_int("FP4_B200_GEMV_CTAS_PER_SM", FP4_STREAM_MINB);
-    const uint32_t max_grid = (uint32_t)(kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm));
-    const uint32_t grid = tiles < max_grid ? tiles : max_grid;
-    p.upt = ((uint32_t)K + 511) / 512;
-    p.tq = tiles / grid; p.tr = tiles % grid;
+    constexpr int NT = sizeof(T) == 4 ? 4 : 2;
+    const Partition pt = partition(tiles, batch, K, NT);
+    const uint32_t grid = pt.grid, ring = pt.ring;
+    p.upt = pt.upt; p.tq = pt.tq; p.tr = pt.tr; p.ring = pt.ring;
     p.by_upt = FastDiv(p.upt);
-    // ring depth: no deeper than a warp has units, no larger than shared memory allows
-    const size_t fixed = fixed_smem_bytes(batch, K, sizeof(T) == 4 ? 4 : 2);
-    const uint32_t units_per_warp = ((p.tq + (p.tr ? 1u : 0u)) * p.upt + kW - 1) / kW;
-    static const int smem_cap = env_int("FP4_B200_GEMV_SMEM_KB", (int)(kMaxSmem / 1024 / FP4_STREAM_MINB)) * 1024;
-    uint32_t ring = (uint32_t)(((size_t)smem_cap - fixed) / ((size_t)kW * kSlot));
-    if (ring > units_per_warp) ring = units_per_warp;
-    if (ring > (uint32_t)max_ring) ring = (uint32_t)max_ring;
-    if (ring > kMaxRing) ring = kMaxRing;
-    if (ring < 1) ring = 1;
-    p.ring = ring;
+    const size_t fixed = fixed_smem_bytes(batch, K, NT);
     // how much of the first slot goes out before griddepcontrol.wait: the x loads queue behind those bytes.
     // Where x staging is short (one chunk per thread) and every SM streams, half a slot measured 2-3 % faster;
     // small grids and long K (more chunks of x per thread) want the whole slot

@@ -105,11 +105,13 @@ def code_is_bnb_fp4(code: torch.Tensor) -> bool:
     hit = _code_cache.get(key)
     if hit is not None and hit[0]() is code and hit[1] == code._version:
         return hit[2]
-    if torch.cuda.is_current_stream_capturing():
+    if code.is_cuda and torch.cuda.is_current_stream_capturing():
         return False  # cannot read the table during capture: take the generic kernel
+    # compared by VALUE: bitsandbytes builds QuantState.code from a Python list whose entry 8 is the int literal
+    # -0, i.e. +0.0, while the reference's table has -0.0 there; the sign of a zero weight changes no sum
     ref = torch.tensor(BNB_FP4_CODE, dtype=torch.float32)
     ok = bool(code.numel() == 16 and code.dtype == torch.float32
-              and torch.equal(code.detach().float().cpu().view(torch.int32), ref.view(torch.int32)))
+              and torch.equal(code.detach().reshape(-1).cpu(), ref))
     _code_cache[key] = (weakref.ref(code, lambda _r, k=key: _code_cache.pop(k, None)),
                         code._version, ok)
     return ok
@@ -385,7 +387,7 @@ class GroupLauncher:
     """Pre-validated launcher for a group of layers that share the input (see GemvLauncher): the pointer
     arrays of fp4_b200_gemv_grouped are built once, a call allocates the outputs and fills in their pointers."""
     __slots__ = ("keep", "n", "pk", "am", "bi", "ou", "ns", "n_outs", "k", "blocksize", "dt", "dtcode", "dev",
-                 "idx", "unsupported")
+                 "idx", "unsupported", "handle")
 
     def __init__(self, Bs, absmaxes, blocksize, dtype, Bshapes, biases=None):
         self.dt = get_scalar_type(dtype)
@@ -414,6 +416,19 @@ class GroupLauncher:
         self.blocksize, self.dtcode = int(blocksize), _CODE_OF[self.dt]
         self.dev, self.idx = Bs[0].device, Bs[0].device.index
         self.unsupported = set()  # batch sizes the grouped kernel refused (FP4_B200_ERR_UNSUPPORTED)
+        # prepared group handle of the C-ABI: the constants are bound once
+        self.handle = lib.fp4_b200_layer_create_grouped(n, self.pk, self.am, None, self.bi, self.ns, self.k,
+                                                        self.blocksize, self.dtcode, _lib.FLAG_CODE_IS_BNB_FP4)
+        if not self.handle:
+            raise RuntimeError("fp4_b200_layer_create_grouped failed")
+
+    def __del__(self):
+        try:
+            h, self.handle = getattr(self, "handle", None), None
+            if h and lib is not None:
+                lib.fp4_b200_layer_destroy(h)
+        except Exception:  # noqa: BLE001 - interpreter shutdown: the library may already be gone
+            pass
 
     def __call__(self, A: torch.Tensor, batch: int):
         """A: contiguous [..., K] of the launcher's dtype on the launcher's (current) device; None = unsupported."""
@@ -424,8 +439,7 @@ class GroupLauncher:
         for i, o in enumerate(outs):
             self.ou[i] = o.data_ptr()
         st = torch._C._cuda_getCurrentRawStream(self.idx)
-        rc = lib.fp4_b200_gemv_grouped(A.data_ptr(), self.n, self.pk, self.am, self.bi, self.ou, self.ns, batch,
-                                       self.k, self.blocksize, self.dtcode, _lib.FLAG_CODE_IS_BNB_FP4, st)
+        rc = lib.fp4_b200_layer_gemv_grouped(self.handle, A.data_ptr(), self.ou, batch, None, st)
         if rc == -7:
             self.unsupported.add(batch)
             return None
