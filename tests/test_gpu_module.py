@@ -1,0 +1,202 @@
+"""GPU tests of the callers and formats either side of the hot path: model surgery, grouped
+projections, state_dict / checkpoint format, tensor-parallel loading, and the reference's qlinear* ops.  The CPU
+oracle is the checker; every compute call goes through libfp4_b200.so."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import oracle
+import torch_bnb_fp4
+import torch_bnb_fp4_ext as ext
+from helpers import normwise, to_dev
+from torch_bnb_fp4_b200 import bnb_compat
+from torch_bnb_fp4_b200.parallel import ColumnParallelFP4Linear, RowParallelFP4Linear
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- reference ops qlinear* (csrc/torch_fp4.cpp:64-103)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows", [1, 3, 64])
+def test_qlinear_ops_match_oracle(cuda, dtype, rows):
+    """dequant + linear inside the op; the codebook variants dequantise the WHOLE weight (the reference passes the
+    byte count as the element count and leaves the second half uninitialised: SURVEY N3)."""
+    M, N = 192, 256  # out_features, in_features
+    rng = np.random.default_rng(rows)
+    w = (rng.standard_normal(M * N) * 0.05).astype(np.float32)
+    packed, absmax = oracle.quantize(w, 64)
+    code = oracle.bnb_code()
+    x32 = rng.standard_normal((rows, N)).astype(np.float32)
+    bias32 = rng.standard_normal(M).astype(np.float32) * 0.1
+    x = to_dev(x32, cuda, dtype)
+    bias = to_dev(bias32, cuda, dtype)
+    A, am, cd = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda), to_dev(code, cuda)
+    xr, br = x.float().cpu().numpy(), bias.float().cpu().numpy()
+    exact = oracle.linear_f64(xr, packed, absmax, code, None, M, N, 64)
+    exact_b = oracle.linear_f64(xr, packed, absmax, code, br, M, N, 64)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2  # 16-bit: weights are rounded to T before the GEMM, as the reference
+    outs = {"qlinear": (ext.qlinear(x, A, am, M, N, 64), exact),
+            "qlinear_bias": (ext.qlinear_bias(x, A, am, M, N, 64, bias), exact_b),
+            "qlinear_codebook": (ext.qlinear_codebook(x, A, am, cd, M, N, 64), exact),
+            "qlinear_codebook_bias": (ext.qlinear_codebook_bias(x, A, am, cd, M, N, 64, bias), exact_b)}
+    for name, (y, ref) in outs.items():
+        assert y.shape == (rows, M) and y.dtype == dtype, name
+        assert normwise(y.float().cpu().numpy(), ref) <= tol, name
+    # the last output rows depend on the second half of the packed bytes: they must be right too
+    y = outs["qlinear_codebook"][0].float().cpu().numpy()
+    assert normwise(y[:, M // 2:], exact[:, M // 2:]) <= tol
+
+
+def test_reduced_precision_linear_module_path(cuda):
+    """allow_reduced_precision_linear=True (reference __init__.py:391-396, 494-558) reaches qlinear_codebook*."""
+    torch.manual_seed(3)
+    w = (torch.randn(128, 256) * 0.05).to(cuda)
+    b = (torch.randn(128) * 0.1).to(cuda)
+    lin = bnb_compat.make_quantized_linear(w, b)
+    st = lin.weight.quant_state
+    qd = torch_bnb_fp4.QuantData(lin.weight.data, st, st.shape, lin, allow_reduced_precision_linear=True)
+    x = torch.randn(40, 256, device=cuda, dtype=torch.float16)
+    qd.set_compute_type(x)
+    y = qd.qlinear(x)
+    ref = torch.nn.functional.linear(x.float(), qd.dequantize().float(), b.half().float())
+    assert normwise(y.float().cpu().numpy(), ref.cpu().numpy()) <= 5e-3
+
+
+# ---------------------------------------------------------------- model surgery
+class _SanityModel(nn.Module):  # reference sanity_check.py:38-50: the SAME two modules registered four times
+    def __init__(self, in_dim, hidden, num_hidden, out_dim):
+        super().__init__()
+        self.in_proj = nn.Linear(in_dim, hidden)
+        self.blocks = nn.Sequential(*([nn.GELU(), nn.Linear(hidden, hidden)] * num_hidden))
+        self.out_proj = nn.Linear(hidden, out_dim)
+
+    def forward(self, x):
+        return self.out_proj(self.blocks(self.in_proj(x)))
+
+
+def test_surgery_replaces_every_alias(cuda):
+    """reference quirk: named_children() de-duplicates, so only blocks[1] is swapped and blocks[3], [5], [7] keep
+    calling the unquantised nn.Linear (sanity_check.py:42-44, __init__.py:829).  Here every alias is swapped, and
+    stays ONE shared layer."""
+    torch.manual_seed(10)
+    model = _SanityModel(768, 512, 4, 64).to(cuda).half()
+    out = torch_bnb_fp4.recursively_replace_with_fp4_linear(model, as_dtype=torch.float16)
+    lins = [m for m in out.blocks if not isinstance(m, nn.GELU)]
+    assert len(lins) == 4 and all(isinstance(m, torch_bnb_fp4.TorchFP4Linear) for m in lins)
+    assert all(m is lins[0] for m in lins)
+    assert not any(type(m) is nn.Linear for m in out.modules())
+    x = torch.randn(1, 768, device=cuda, dtype=torch.float16)
+    assert torch.isfinite(out(x)).all()
+
+
+class _Block(nn.Module):
+    def __init__(self, h, inter, kv):
+        super().__init__()
+        self.q_proj, self.k_proj, self.v_proj = nn.Linear(h, h, bias=False), nn.Linear(h, kv, bias=False), nn.Linear(h, kv, bias=False)
+        self.o_proj = nn.Linear(h, h, bias=False)
+        self.gate_proj, self.up_proj = nn.Linear(h, inter, bias=False), nn.Linear(h, inter, bias=False)
+        self.down_proj = nn.Linear(inter, h, bias=False)
+
+    def forward(self, x):
+        q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        o = self.o_proj(q)
+        h = self.down_proj(torch.nn.functional.silu(self.gate_proj(o)) * self.up_proj(o))
+        return h, k, v
+
+
+def test_surgery_groups_projections_by_default(cuda):
+    """recursively_replace_with_fp4_linear leaves q/k/v and gate/up sharing one launch each; results equal the
+    ungrouped conversion (same kernel, same per-row arithmetic)."""
+    torch.manual_seed(4)
+    blk = _Block(1024, 2816, 256).to(cuda).half()
+    import copy
+    a = torch_bnb_fp4.recursively_replace_with_fp4_linear(copy.deepcopy(blk), as_dtype=torch.float16)
+    b = torch_bnb_fp4.recursively_replace_with_fp4_linear(copy.deepcopy(blk), as_dtype=torch.float16,
+                                                          group_projections_=False)
+    assert type(a.q_proj).__name__ == "_GroupMember" and type(a.up_proj).__name__ == "_GroupMember"
+    assert isinstance(b.q_proj, torch_bnb_fp4.TorchFP4Linear)
+    for rows in (1, 2, 5, 300):
+        x = torch.randn(rows, 1024, device=cuda, dtype=torch.float16)
+        for ya, yb in zip(a(x), b(x)):
+            assert normwise(ya.float().cpu().numpy(), yb.float().cpu().numpy()) <= 2e-3
+    # the parked sibling outputs do not survive the block's forward
+    assert a.q_proj._group[0]._cache_x is None
+
+
+def test_positive_zero_codebook_takes_the_fast_kernels(cuda):
+    """bitsandbytes' QuantState.code has +0.0 at index 8: still the bitsandbytes table."""
+    torch.manual_seed(5)
+    w = (torch.randn(1024, 1024) * 0.03).to(cuda)
+    lin = bnb_compat.make_quantized_linear(w)
+    code = lin.weight.quant_state.code.clone()
+    code[8] = 0.0
+    lin.weight.quant_state.code = code
+    m = torch_bnb_fp4.TorchFP4Linear(lin)
+    assert m.quant_data._code_is_std
+    x = torch.randn(1, 1024, device=cuda, dtype=torch.bfloat16)
+    ref = torch.nn.functional.linear(x.float(), m.quant_data.dequantize().float())
+    assert normwise(m(x).float().cpu().numpy(), ref.cpu().numpy()) <= 6e-3
+
+
+# ---------------------------------------------------------------- state_dict / checkpoint format
+@pytest.mark.parametrize("nested", [False, True])
+def test_module_state_dict_round_trip(cuda, nested):
+    """model.state_dict() carries the bitsandbytes 4-bit keys; load_state_dict() into a differently initialised
+    converted model reproduces the outputs bit for bit."""
+    torch.manual_seed(6)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        net = nn.Sequential(nn.Linear(512, 1024), nn.GELU(), nn.Linear(1024, 256)).to(cuda)
+        for i in (0, 2):
+            net[i] = torch_bnb_fp4.TorchFP4Linear(
+                bnb_compat.make_quantized_linear(net[i].weight.data, net[i].bias.data, compress_statistics=nested))
+        return net
+    a, b = make(1), make(2)
+    sd = a.state_dict()
+    assert "0.weight" in sd and "0.weight.absmax" in sd and "0.weight.quant_state.bitsandbytes__fp4" in sd
+    assert ("2.weight.nested_absmax" in sd) == nested and sd["0.weight"].dtype == torch.uint8
+    x = torch.randn(3, 512, device=cuda, dtype=torch.bfloat16)
+    assert not torch.equal(a(x), b(x))
+    res = b.load_state_dict({k: v.cpu() for k, v in sd.items()})
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(a(x), b(x))
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        bad = dict(sd)
+        for k in list(bad):
+            if k.startswith("0."):
+                bad[k] = sd[k.replace("0.", "2.", 1)]
+        b.load_state_dict(bad)
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_tp_shards_cut_at_load(cuda, nested):
+    """from_quantized_state_dict(..., tp_rank, tp_world, tp_mode): the shard equals the one cut from the loaded
+    full layer (bit for bit), and the shards' outputs recombine to the full layer's output."""
+    torch.manual_seed(7)
+    N, K, tp = 1024, 2048, 4
+    w = (torch.randn(N, K) * 0.03).to(cuda)
+    bias = (torch.randn(N) * 0.1).to(cuda)
+    full = torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w, bias, compress_statistics=nested))
+    sd = {k: v.cpu() for k, v in full.quantized_state_dict("m.").items()}
+    x = torch.randn(2, K, device=cuda, dtype=torch.bfloat16)
+    y_full = full(x).float()
+    cols, rows = [], []
+    for r in range(tp):
+        c = torch_bnb_fp4.TorchFP4Linear.from_quantized_state_dict(sd, "m.", device=cuda, tp_rank=r, tp_world=tp,
+                                                                 tp_mode="column")
+        want = ColumnParallelFP4Linear(full, rank=r, tp=tp).local
+        assert torch.equal(c.quant_data.A, want.quant_data.A) and torch.equal(c.quant_data.absmax, want.quant_data.absmax)
+        assert (c.out_features, c.in_features) == (N // tp, K)
+        cols.append(c(x))
+        rw = torch_bnb_fp4.TorchFP4Linear.from_quantized_state_dict(sd, "m.", device=cuda, tp_rank=r, tp_world=tp,
+                                                                  tp_mode="row")
+        want = RowParallelFP4Linear(full, rank=r, tp=tp).local
+        assert torch.equal(rw.quant_data.A, want.quant_data.A) and torch.equal(rw.quant_data.absmax, want.quant_data.absmax)
+        assert (rw.quant_data.bias is not None) == (r == 0)
+        rows.append(rw(x[:, r * (K // tp):(r + 1) * (K // tp)].contiguous()).float())
+    # the same rows, possibly summed in another warp order: within one bf16 rounding
+    assert normwise(torch.cat(cols, dim=-1).float().cpu().numpy(), y_full.cpu().numpy()) <= 8e-3
+    y_row = sum(rows)
+    assert normwise(y_row.cpu().numpy(), y_full.cpu().numpy()) <= 1e-2

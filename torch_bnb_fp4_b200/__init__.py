@@ -271,6 +271,7 @@ class TorchFP4Linear(nn.Module):
         self.out_features = lin.out_features
         self.use_codebook_dequant = use_codebook_dequant
         self.name = name
+        self._materialize_nested = materialize_nested_absmax
         w = lin.weight
         if not (isinstance(w, Params4bit) or hasattr(w, "quant_state")):
             raise ValueError("Linear is not a bnb linear and is not quantized, and I have no idea "
@@ -306,20 +307,80 @@ class TorchFP4Linear(nn.Module):
         return out
 
     @classmethod
-    def from_quantized_state_dict(cls, sd: dict, prefix: str = "", device="cuda", **kw) -> "TorchFP4Linear":
+    def from_quantized_state_dict(cls, sd: dict, prefix: str = "", device="cuda", tp_rank: int = 0,
+                                  tp_world: int = 1, tp_mode: Optional[str] = None, **kw) -> "TorchFP4Linear":
         """Rebuild a layer from the bitsandbytes 4-bit keys (`weight`, `weight.absmax`, `weight.quant_map`,
-        `weight.quant_state.bitsandbytes__fp4`, optional `weight.nested_*`, `bias`)."""
+        `weight.quant_state.bitsandbytes__fp4`, optional `weight.nested_*`, `bias`).
+
+        With ``tp_world > 1`` only this rank's shard is built: ``tp_mode="column"`` keeps rows
+        [rank*N/tp, (rank+1)*N/tp) (q/k/v/gate/up), ``"row"`` keeps columns [rank*K/tp, ...) of every row (o/down;
+        the bias stays with rank 0, which adds it once before the reduction).  The cut is made on the HOST copy
+        of the checkpoint tensors, so the full weight never reaches the GPU; a nested absmax is materialised
+        first because its 256-block grouping does not line up with shard boundaries."""
         w = sd[prefix + "weight"]
         comp = {k[len(prefix) + len("weight."):]: v for k, v in sd.items() if k.startswith(prefix + "weight.")}
-        qs = bnb_compat.quant_state_from_dict(comp, device=device)
-        out_f, in_f = int(qs.shape[0]), int(qs.shape[1])
         bias = sd.get(prefix + "bias")
+        if tp_world > 1:
+            from .parallel import shard_column, shard_row
+            if tp_mode not in ("column", "row"):
+                raise ValueError("tp_mode must be 'column' or 'row' when tp_world > 1")
+            qs_full = bnb_compat.quant_state_from_dict(comp, device=None)
+            N, K, bs = int(qs_full.shape[0]), int(qs_full.shape[1]), int(qs_full.blocksize)
+            absmax = qs_full.absmax
+            if qs_full.nested:  # decode on the device (bit-exact kernel), slice on the host
+                nd = _ext.make_nested(absmax.to(device).contiguous(), qs_full.state2.code.float().to(device).contiguous(),
+                                      qs_full.state2.absmax.float().to(device).contiguous(),
+                                      float(qs_full.offset), qs_full.state2.blocksize)
+                absmax = _ext.absmax_denest(nd, (N * K + bs - 1) // bs, torch.device(device)).cpu()
+            absmax = absmax.float()
+            if tp_mode == "column":
+                p, a, n = shard_column(w, absmax, N, K, tp_rank, tp_world, bs)
+                shape = (n, K)
+                if bias is not None:
+                    bias = bias[tp_rank * n:(tp_rank + 1) * n]
+            else:
+                p, a, k = shard_row(w, absmax, N, K, tp_rank, tp_world, bs)
+                shape = (N, k)
+                if tp_rank != 0:
+                    bias = None
+            qs = bnb_compat.QuantState(absmax=a.to(device), shape=torch.Size(shape), code=qs_full.code.to(device),
+                                       blocksize=bs, quant_type="fp4", dtype=qs_full.dtype)
+            w = p
+        else:
+            qs = bnb_compat.quant_state_from_dict(comp, device=device)
+        out_f, in_f = int(qs.shape[0]), int(qs.shape[1])
         lin = bnb_compat.LinearFP4(in_f, out_f, bias=bias is not None, compress_statistics=bool(qs.nested))
         lin.weight = Params4bit(w.to(device).contiguous().view(-1, 1), requires_grad=False, quant_state=qs,
                                 blocksize=qs.blocksize, compress_statistics=bool(qs.nested), quant_type="fp4")
         if bias is not None:
             lin.bias = nn.Parameter(bias.detach().clone().to(device), requires_grad=False)
         return cls(lin, **kw)
+
+    # nn.Module.state_dict() / load_state_dict(): the same keys, written and read the way bitsandbytes' Linear4bit
+    # does (_save_to_state_dict adds the quant-state components next to `weight`), so a converted model saves and
+    # reloads with torch.save(model.state_dict()) like any other module.
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, v in self.quantized_state_dict(prefix).items():
+            destination[k] = v if keep_vars else v.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        if prefix + "weight" not in state_dict:
+            missing_keys.append(prefix + "weight")
+            return
+        try:
+            new = TorchFP4Linear.from_quantized_state_dict(
+                state_dict, prefix, device=self.quant_data.A.device, use_codebook_dequant=self.use_codebook_dequant,
+                name=self.name, materialize_nested_absmax=self._materialize_nested)
+        except Exception as e:  # noqa: BLE001
+            error_msgs.append(f"While loading {prefix}weight: {e}")
+            return
+        if (new.in_features, new.out_features) != (self.in_features, self.out_features):
+            error_msgs.append(f"size mismatch for {prefix}weight: checkpoint holds "
+                              f"{new.out_features}x{new.in_features}, the module is "
+                              f"{self.out_features}x{self.in_features}")
+            return
+        self.lin, self.quant_data = new.lin, new.quant_data
 
     @classmethod
     def from_linear(cls, linear, use_codebook_dequant: bool = False, name: str = "") -> "TorchFP4Linear":
@@ -391,6 +452,8 @@ class _GroupMember(nn.Module):
             out = g._cache[self.index]
             if out is not None:
                 g._cache[self.index] = None
+                if all(o is None for o in g._cache):  # last sibling served: drop the references
+                    g._cache_x = None
                 return out
         k = x.shape[-1]
         rows = x.numel() // k if k else 0
@@ -430,6 +493,13 @@ def group_projections(model: nn.Module, names=_GROUPABLE_NAMES) -> int:
                 continue
             for i, n in enumerate(group_names):
                 setattr(parent, n, _GroupMember(grp, i))
+
+            # parked sibling outputs never outlive the block's forward: a later call that happens to pass the
+            # same tensor object again (a static buffer refilled through a raw pointer, which the version counter
+            # does not see) starts from a fresh launch
+            def _drop(_m, _i, _o, g=grp):
+                g._cache_x, g._cache = None, [None] * len(g._cache)
+            parent.register_forward_hook(_drop)
             made += 1
     return made
 
@@ -477,23 +547,37 @@ def recursively_replace_with_fp4_linear(
     device: torch.device = torch.device("cuda" if torch.cuda.is_available() else "cpu"),
     return_final_module: bool = True, only_replace_bnb_layers: bool = False,
     ignore_layer_names: List[str] = ["lm_head"], parent="", debug: bool = False,
+    group_projections_: bool = True, _memo: Optional[dict] = None,
 ) -> Optional[T_Model]:
     """Swap every nn.Linear / LinearFP4 / Linear4bit below `module` for a TorchFP4Linear
-    (reference :781-922; same keyword arguments and defaults)."""
+    (reference :781-922; same keyword arguments and defaults).
+
+    Two differences, both on purpose.  (1) The reference walks ``named_children()``, which yields a module that is
+    registered under several names only ONCE: in ``nn.Sequential(*([act, lin] * 4))`` (its own sanity model,
+    sanity_check.py:42-44) only the first alias is swapped and the other three keep calling the unquantised
+    nn.Linear.  Here every alias gets the same replacement.  (2) ``group_projections_`` (default on, top-level call
+    only): sibling q/k/v and gate/up projections of decoder blocks share one fused launch afterwards
+    (``group_projections``); outputs are the same up to fp32 summation order."""
     dev_type = device.type if hasattr(device, "type") else str(device).split(":")[0]
     assert dev_type == "cuda", "Device type must be cuda!"
     prefix = parent + "." if parent != "" else ""
     swapped_plain = False
-    for name, child in module.named_children():
+    memo = {} if _memo is None else _memo  # id(original module) -> its replacement: aliases stay aliases
+    for name, child in list(module._modules.items()):
+        if child is None:
+            continue
         child_name = prefix + name
         if check_if_name_contained_in_list(name, ignore_layer_names):
             if debug:
                 print(f"Ignoring name: {child_name}, as it is in the ignore list")
             continue
+        if id(child) in memo:
+            module._modules[name] = memo[id(child)]
+            continue
         if isinstance(child, (LinearFP4, Linear4bit)):
             if debug:
                 print(f"Replacing BNB layer {child_name} swapping with TorchFP4Linear.")
-            module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant, child_name)
+            memo[id(child)] = module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant, child_name)
         elif isinstance(child, nn.Linear):
             if only_replace_bnb_layers:
                 if debug:
@@ -501,13 +585,16 @@ def recursively_replace_with_fp4_linear(
             else:
                 if debug:
                     print(f"Replacing {child_name} with BNB linear, and then swapping with TorchFP4Linear.")
-                module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant, child_name)
+                memo[id(child)] = module._modules[name] = _to_fp4(child, device, as_dtype, use_codebook_dequant,
+                                                                  child_name)
                 swapped_plain = True
         elif isinstance(child, nn.Module):
+            memo[id(child)] = child  # visited: a shared sub-tree is converted once
             recursively_replace_with_fp4_linear(
                 child, as_dtype=as_dtype, use_codebook_dequant=use_codebook_dequant, device=device,
                 return_final_module=False, only_replace_bnb_layers=only_replace_bnb_layers,
-                ignore_layer_names=ignore_layer_names, parent=child_name, debug=debug)
+                ignore_layer_names=ignore_layer_names, parent=child_name, debug=debug,
+                group_projections_=False, _memo=memo)
     if isinstance(module, (LinearFP4, Linear4bit)):
         module = _to_fp4(module, device, as_dtype, use_codebook_dequant, parent)
     elif isinstance(module, nn.Linear) and not only_replace_bnb_layers:
@@ -515,5 +602,7 @@ def recursively_replace_with_fp4_linear(
         swapped_plain = True
     if swapped_plain:
         torch.cuda.empty_cache()
+    if group_projections_ and _memo is None and isinstance(module, nn.Module):
+        group_projections(module)
     if return_final_module:
         return module
