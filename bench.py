@@ -6,24 +6,31 @@
 Workload (BASELINE.json configs[2], the one the metric is quoted on): the Mistral-7B linear stack at
 batch 1 - 32 layers x {q 4096x4096, k 1024x4096, v 1024x4096, o 4096x4096, gate 14336x4096,
 up 14336x4096, down 4096x14336}, blocksize 64, fp32 absmax, bf16 activations, random-init packed weights
-(synthetic; there is no network for checkpoints).  One STEP = one decode token = 224 fused dequant-GEMVs
-chained through their outputs (h -> q,k,v; q -> o; o -> gate,up; up -> down -> next layer), i.e. the
-data dependence of a real decoder with the attention / norm / activation kernels (not part of this
+(synthetic; there is no network for checkpoints).  One STEP = one decode token = the seven projections of every
+decoder layer chained through their outputs (h -> q,k,v; q -> o; o -> gate,up; up -> down -> next layer), i.e.
+the data dependence of a real decoder with the attention / norm / activation kernels (not part of this
 library) left out.  The 3.93 GB of weights exceed L2 (126 MB) 31x, so every step streams from HBM.
+
+The model is built the way a user of the drop-in API builds it: decoder blocks of quantised bitsandbytes-style
+LinearFP4 layers put through recursively_replace_with_fp4_linear(), whose default now makes the q/k/v and the
+gate/up projections of a block share one fused launch each (group_projections); the step function still calls
+the seven projections one by one.  `launches_per_step` is what the library counted for one step
+(fp4_b200_launch_count).  `ungrouped_launches` is the same stack with one launch per linear (224 per token: the
+reference's granularity, round 1's headline).
 
 metric / value: whole-job algorithmic GB/s = (0.5625 B per weight + activations) * steps / device time,
 timed with CUDA events around K CUDA-graph replays.  `tok_per_s` = steps / time.
-e2e: the same through the public API (TorchFP4Linear modules under GraphedCallable) with, every step,
-the host->device copy of the input activation from pinned memory and the device->host read of the
-result inside the timed region.
-grouped_launches: the same stack with q/k/v and gate/up each issued as ONE grouped launch (TorchFP4LinearGroup /
-fp4_b200_gemv_grouped; 128 launches per token) - an extension the reference does not have, reported beside
-the headline, never instead of it.
+e2e: the same converted model under GraphedCallable with, every step, the host->device copy of the input
+activation from pinned memory and the device->host read of the result inside the timed region.
+Extra keys at N = 1 (skip with --no-extras): `c1_single_layer` (BASELINE config #1), `sanity_mlp` (config #2:
+the reference's 6-layer MLP at batch 1 / 2 / 16 in three dtypes, eager and graphed, reference extension beside
+it), `gemm_sweep` (config #5: dequant-fused tcgen05 GEMM vs dequant + cuBLAS on 28672x8192, M = 1..4096).
 N > 1 (torchrun): tensor parallel, Megatron style - q/k/v/gate/up column-parallel, o/down row-parallel - strong
 scaling of the same workload.  --tp-mode peer (default): the row-parallel partial sums are pushed into every
 rank's symmetric-memory buffer by the GEMV itself and summed while the next launch stages x (PeerExchange /
 fp4_b200_gemv_grouped_tp): no collective launches except one all_reduce per token for the final hidden state;
-the NCCL all_reduce-per-layer variant is timed in the same run and reported as `nccl_allreduce_variant`.
+the NCCL all_reduce-per-layer variant is timed in the same run, the two results are compared
+(max_rel_diff_peer_vs_nccl <= 5e-2 asserted) and reported as `nccl_allreduce_variant`.
 --workload llama70b: BASELINE config #4 shapes (80 layers, 38.5 GB of FP4 linears), for reference.
 
 --impl reference: the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference/csrc)
@@ -79,83 +86,83 @@ def gemv_bytes(N, K, batch=1, act=2):
     return N * K // 2 + 4 * (N * K // BLOCKSIZE) + batch * K * act + batch * N * act
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("MAX", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mask, flush=True)
+    except Exception:
+        pass
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every 4 ms (the timed
-    region of the default run is ~80 ms, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region by a SEPARATE process polling NVML every 2 ms
+    (nvidia-smi -lms cannot resolve a region of tens of milliseconds; a sampler thread inside this process would
+    share the interpreter with the thread that launches the graphs).  Only samples taken between __enter__ and
+    __exit__ count."""
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    _proc = None
+    _lines = None
 
     def __init__(self, index=0, enabled=True):
-        self.rows, self.proc, self.index = [], None, index
-        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
-        self._stop = threading.Event()
-        self.enabled = enabled  # only the rank that prints samples: eight processes polling the driver perturb it
+        self.index, self.enabled = index, enabled
+        self.t0 = self.t1 = None
 
-    def _nvml_loop(self, nv, h):
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:  # noqa: BLE001 - older binding name
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.BITS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.004)
+    @classmethod
+    def start(cls, index):
+        """launch the sampler process once, well before the timed region (its start-up is not free)"""
+        if cls._proc is not None:
+            return
+        try:
+            cls._proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            cls._lines = []
+            threading.Thread(target=lambda: [cls._lines.append(ln) for ln in cls._proc.stdout], daemon=True).start()
+        except Exception:  # noqa: BLE001
+            cls._proc = None
+
+    @classmethod
+    def stop(cls):
+        if cls._proc is not None:
+            cls._proc.terminate()
+            cls._proc = None
 
     def __enter__(self):
-        if not self.enabled:
-            return self
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
-            self.how = "nvml"
-            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
-            self.thread.start()
-            return self
-        except Exception:  # noqa: BLE001
-            self.how = None
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.how = "nvidia-smi"
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+        if self.enabled:
+            ClockSampler.start(self.index)
+            self.t0 = time.time()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *exc):
-        self._stop.set()
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-        if self.how:
-            self.thread.join(timeout=2)
+        self.t1 = time.time()
 
     def summary(self):
-        if self.how == "nvml":
-            sm = sorted(self.sm)
-            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 4 ms period"}
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
+        if not self.enabled or ClockSampler._lines is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        time.sleep(0.01)
+        sm, reasons, mx = [], set(), None
+        for ln in list(ClockSampler._lines):
+            f = ln.split()
+            if f and f[0] == "MAX":
+                mx = float(f[1])
+            elif len(f) == 3 and self.t0 <= float(f[0]) <= self.t1:
+                sm.append(float(f[1]))
+                for bit, name in self.BITS.items():
+                    if int(f[2]) & bit:
+                        reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "NVML polled every 2 ms by a separate process"}
 
 
 def synth_layer(N, K, dev, gen):
@@ -166,11 +173,20 @@ def synth_layer(N, K, dev, gen):
     return packed, absmax
 
 
-def build_stack(cfg, dev, rank=0, tp=1, seed=0):
-    """The model as TorchFP4Linear modules (public API); TP shards when tp > 1."""
-    import torch_bnb_fp4
+class Block(torch.nn.Module):
+    """The linears of one decoder layer under their usual names (what model surgery sees in an HF Mistral/Llama)."""
+
+    def __init__(self, mods):
+        super().__init__()
+        self.q_proj, self.k_proj, self.v_proj, self.o_proj = mods["q"], mods["k"], mods["v"], mods["o"]
+        self.gate_proj, self.up_proj, self.down_proj = mods["gate"], mods["up"], mods["down"]
+
+
+def build_bnb_layers(cfg, dev, rank=0, tp=1, seed=0):
+    """Per decoder layer a dict of QUANTISED bitsandbytes-style LinearFP4 (synthetic packed weights); TP shards
+    when tp > 1.  Returns (layers, algorithmic bytes per token of the unsharded model)."""
     from torch_bnb_fp4_b200 import bnb_compat, ext
-    from torch_bnb_fp4_b200.parallel import ColumnParallelFP4Linear, RowParallelFP4Linear, shard_column, shard_row
+    from torch_bnb_fp4_b200.parallel import shard_column, shard_row
 
     gen = torch.Generator(device=dev).manual_seed(seed)
     code = torch.tensor(ext.BNB_FP4_CODE, dtype=torch.float32, device=dev)
@@ -191,9 +207,17 @@ def build_stack(cfg, dev, rank=0, tp=1, seed=0):
                                        quant_type="fp4", dtype=torch.bfloat16)
             lin.weight = bnb_compat.Params4bit(packed, requires_grad=False, quant_state=st,
                                                blocksize=BLOCKSIZE, compress_statistics=False, quant_type="fp4")
-            mods[name] = torch_bnb_fp4.TorchFP4Linear(lin, name=name)
+            mods[name] = lin
         layers.append(mods)
     return layers, nbytes
+
+
+def build_stack(cfg, dev, rank=0, tp=1, seed=0):
+    """The model as plain TorchFP4Linear modules, one per linear (the reference's granularity: 7 launches per
+    decoder layer); used for the ungrouped line and for tensor parallelism."""
+    import torch_bnb_fp4
+    bnb_layers, nbytes = build_bnb_layers(cfg, dev, rank, tp, seed)
+    return [{k: torch_bnb_fp4.TorchFP4Linear(v, name=k) for k, v in m.items()} for m in bnb_layers], nbytes
 
 
 def make_step(layers, tp):
@@ -216,24 +240,18 @@ def make_step(layers, tp):
     return step
 
 
-def make_step_grouped(layers, tp):
-    """Same computation with q/k/v and gate/up issued as ONE grouped launch each (4 launches per layer)."""
-    import torch.distributed as dist
-
-    import torch_bnb_fp4
-    groups = [(torch_bnb_fp4.TorchFP4LinearGroup([m["q"], m["k"], m["v"]]),
-               torch_bnb_fp4.TorchFP4LinearGroup([m["gate"], m["up"]]), m) for m in layers]
-
+def make_step_blocks(blocks):
+    """The same chain on decoder blocks whose forward calls the seven projections one by one (what an unmodified
+    HF decoder layer does)."""
     def step(h):
-        for qkv, gu, m in groups:
-            q, _, _ = qkv(h)
-            o = m["o"](q)
-            if tp > 1:
-                dist.all_reduce(o)
-            _, up = gu(o)
-            h = m["down"](up)
-            if tp > 1:
-                dist.all_reduce(h)
+        for b in blocks:
+            q = b.q_proj(h)
+            b.k_proj(h)
+            b.v_proj(h)
+            o = b.o_proj(q)
+            b.gate_proj(o)
+            up = b.up_proj(o)
+            h = b.down_proj(up)
         return h
     return step
 
@@ -281,6 +299,17 @@ def time_events(fn, steps):
     return e0.elapsed_time(e1) * 1e-3
 
 
+def launches_of(fn):
+    """kernels the library launches for one eager call of fn (its own bookkeeping: fp4_b200_launch_count)."""
+    from torch_bnb_fp4_b200._lib import lib
+    torch.cuda.synchronize()
+    n0 = lib.fp4_b200_launch_count()
+    with torch.no_grad():
+        fn()
+    torch.cuda.synchronize()
+    return int(lib.fp4_b200_launch_count() - n0)
+
+
 def cpu_baseline_sample(seconds=10.0):
     """Oracle port of dequantize_fp4 + matmul on the host cores: one 4096x4096 batch-1 layer, repeated."""
     import numpy as np
@@ -313,59 +342,216 @@ def traffic_from_profile():
         return None
 
 
+def graph_us(fn, reps=5, inner=1):
+    """device microseconds per call of fn (captured `inner` times into one CUDA graph, best of `reps` replays)"""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s), torch.no_grad():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(inner):
+                fn()
+    g.replay()
+    torch.cuda.synchronize()
+    return min(time_events(g.replay, 1) for _ in range(reps)) / inner * 1e6
+
+
+def eager_us(fn, n=100):
+    with torch.no_grad():
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n * 1e6
+
+
+def _load_ref_ext():
+    try:
+        from oracle.build_ref import load_module
+        return load_module()
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def extra_c1(dev):
+    """BASELINE config #1: ONE 4096x4096 blocksize-64 layer, batch-1 GEMV, weights rotated over 40 buffers
+    (377 MB > 2x L2) so the stream comes from HBM; the reference extension on the same buffers beside it."""
+    import torch_bnb_fp4_ext as ext
+    N = K = 4096
+    nrot = 40
+    gen = torch.Generator(device=dev).manual_seed(1)
+    Ws = [synth_layer(N, K, dev, gen) for _ in range(nrot)]
+    code = torch.tensor(ext.BNB_FP4_CODE, dtype=torch.float32, device=dev)
+    x = torch.randn(1, K, device=dev).bfloat16()
+    it = [0]
+
+    def ours():
+        p, a = Ws[it[0] % nrot]
+        it[0] += 1
+        return ext.gemv_fp4(x, p, a, code, BLOCKSIZE, ext.bfloat16, [N, K])
+    us = graph_us(ours, inner=nrot)
+    out = {"what": "single 4096x4096 bnb-FP4 Linear, batch-1 GEMV, bf16, 40 rotating weight buffers, CUDA graph",
+           "us_per_op": us, "GB_per_s": gemv_bytes(N, K) / us / 1e3}
+    ref = _load_ref_ext()
+    if ref is not None:
+        def theirs():
+            p, a = Ws[it[0] % nrot]
+            it[0] += 1
+            return ref.gemv_fp4(x, p.t(), a, code, BLOCKSIZE, ref.bfloat16, [N, K])
+        us_r = eager_us(lambda: [theirs() for _ in range(nrot)], n=5) / nrot
+        out["reference_ext_us_per_op"] = us_r
+        out["reference_ext_GB_per_s"] = gemv_bytes(N, K) / us_r / 1e3
+        out["reference_ext_note"] = "eager (legacy stream, not graph-capturable), launch rate included"
+    return out
+
+
+def extra_sanity_mlp(dev):
+    """BASELINE config #2 (reference sanity_check.py:65-122, README:100-159): the 6-layer MLP 768 -> 2048 x5 -> 64
+    with GELU, batch 1 (GEMV path), 2 and 16 (GEMM path), fp16 / bf16 / fp32, eager and CUDA-graph replayed; the
+    reference extension driven the way its module drives it (gemv_fp4 + bias for batch 1, codebook dequant +
+    F.linear otherwise) beside it."""
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    ref = _load_ref_ext()
+    dims = [768, 2048, 2048, 2048, 2048, 2048, 64]
+    res = {}
+    for dtype in (torch.float16, torch.bfloat16, torch.float32):
+        torch.manual_seed(10)
+        lins = [torch.nn.Linear(dims[i], dims[i + 1]).to(dev).to(dtype) for i in range(6)]
+        fp4 = [torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(l.weight.data, l.bias.data)) for l in lins]
+        act = torch.nn.GELU()
+
+        def run(layers, x):
+            for i, l in enumerate(layers):
+                x = l(x)
+                if i < 5:
+                    x = act(x)
+            return x
+
+        def ref_layer(m):
+            qd = m.quant_data
+            st = {torch.float16: ref.float16, torch.bfloat16: ref.bfloat16, torch.float32: ref.float32}[dtype]
+            bias = qd.bias.to(dtype)
+
+            def f(x):
+                if x.numel() == x.shape[-1]:
+                    return ref.gemv_fp4(x, qd.A.t(), qd.absmax, qd.code, 64, st, [qd.M, qd.N]) + bias
+                w = ref.dequantize_fp4_codebook(qd.A, qd.absmax, qd.code, qd.M, qd.N, 64, qd.numel, st)
+                return torch.nn.functional.linear(x, w, bias)
+            return f
+        row = {}
+        for b in (1, 2, 16):
+            x = torch.randn(b, 768, device=dev).to(dtype)
+            e = {"dense_eager_us": eager_us(lambda: run(lins, x)), "fp4_eager_us": eager_us(lambda: run(fp4, x)),
+                 "fp4_graph_us": graph_us(lambda: run(fp4, x)), "dense_graph_us": graph_us(lambda: run(lins, x))}
+            if ref is not None:
+                rl = [ref_layer(m) for m in fp4]
+                e["reference_ext_eager_us"] = eager_us(lambda: run(rl, x))
+            row[f"batch{b}"] = e
+        res[str(dtype).replace("torch.", "")] = row
+    return res
+
+
+def extra_gemm_sweep(dev):
+    """BASELINE config #5: prefill sweep on an 8192x28672 weight (out x in = 28672 x 8192, the Llama-70B gate/up
+    orientation), bf16: the dequant-fused tcgen05 GEMM against this library's dequant kernel + cuBLAS."""
+    import torch_bnb_fp4_ext as ext
+    N, K = 28672, 8192
+    gen = torch.Generator(device=dev).manual_seed(2)
+    packed, absmax = synth_layer(N, K, dev, gen)
+    code = torch.tensor(ext.BNB_FP4_CODE, dtype=torch.float32, device=dev)
+    rows = {}
+    for M in (1, 8, 16, 64, 128, 256, 512, 1024, 2048, 4096):
+        x = torch.randn(M, K, device=dev).bfloat16()
+        if M <= 8:
+            fused = graph_us(lambda: ext.gemv_fp4(x, packed, absmax, code, 64, ext.bfloat16, [N, K]), inner=4)
+        else:
+            fused = graph_us(lambda: ext.gemm_fp4(x, packed, absmax, code, N, K, 64), inner=2)
+        pair = graph_us(lambda: torch.nn.functional.linear(x, ext.dequantize_fp4(packed, absmax, 64, N, K, ext.bfloat16)),
+                        inner=2)
+        rows[str(M)] = {"fused_us": fused, "dequant_cublas_us": pair, "speedup": pair / fused,
+                        "fused_TFLOPs": 2.0 * M * N * K / fused / 1e6}
+    return rows
+
+
 def run_ours(args, rank, world):
     import torch.distributed as dist
 
+    import torch_bnb_fp4
     from torch_bnb_fp4_b200.graph import GraphedCallable
 
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    if rank == 0:
+        ClockSampler.start(dev.index)
     cfg = dict(MISTRAL)
     if args.workload == "c1":
         cfg = dict(hidden=4096, inter=4096, kv=4096, layers=10)  # 70 x 4096x4096 layers = 660 MB > L2
     elif args.workload == "llama70b":
         cfg = dict(LLAMA70B)
-    layers, nbytes = build_stack(cfg, dev, rank, world)
-    launches_per_step = len(layers) * 7
-    step = make_step(layers, world)
+    bnb_layers, nbytes = build_bnb_layers(cfg, dev, rank, world)
+    # the ungrouped modules (the reference's granularity) share the packed buffers with the converted model below
+    layers = [{k: torch_bnb_fp4.TorchFP4Linear(v, name=k) for k, v in m.items()} for m in bnb_layers]
     h0 = torch.randn(1, cfg["hidden"], device=dev).bfloat16()
-    tp_mode = "none" if world == 1 else "nccl all_reduce after every row-parallel layer"
+    tp_mode = "none"
     nccl_line = None
-    if world > 1 and args.tp_mode == "peer":
-        # headline for N > 1: the peer-memory exchange; the NCCL variant is timed beside it
-        from torch_bnb_fp4_b200.parallel import PeerExchange
-        runner_n = GraphedCallable(step, [h0], warmup=3)
-        for _ in range(args.warmup):
-            runner_n.graph.replay()
-        dist.barrier(); torch.cuda.synchronize()
-        t_n = time_events(runner_n.graph.replay, args.steps)
-        v = torch.tensor([t_n], device=dev, dtype=torch.float64)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        nccl_line = {"tok_per_s": args.steps / float(v.item()), "ms_per_step": float(v.item()) / args.steps * 1e3}
-        ref_out = runner_n(h0).float().clone()
-        del runner_n
-        try:
-            exchange = PeerExchange(cfg["hidden"], torch.bfloat16, dev)
-            step_p = make_step_peer(layers, exchange)
-            with torch.no_grad():
-                step_p(h0)  # shapes outside the streaming kernel raise here (e.g. K/tp % 512 != 0 at tp 8)
-            ok = torch.ones(1, device=dev)
-        except Exception as e:  # noqa: BLE001
-            print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL", file=sys.stderr)
-            ok = torch.zeros(1, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() > 0:
-            step = step_p
-            tp_mode = ("row-parallel partial sums exchanged through peer (symmetric) memory and summed in the "
-                       "consumer's x staging; q/k/v and gate/up grouped; one NCCL all_reduce per token for the "
-                       "final hidden state")
-        else:
-            nccl_line = None
+    exchange = None
+    if world == 1:
+        # headline: the model as the drop-in API leaves it - decoder blocks of bitsandbytes LinearFP4 layers put
+        # through recursively_replace_with_fp4_linear() (which, by default, makes q/k/v and gate/up share one
+        # launch each), then called projection by projection like an unmodified HF decoder layer
+        model = torch.nn.ModuleList([Block(m) for m in bnb_layers])
+        model = torch_bnb_fp4.recursively_replace_with_fp4_linear(model, as_dtype=torch.bfloat16, device=dev)
+        step = make_step_blocks(list(model))
+        how = "recursively_replace_with_fp4_linear(model) [default: q/k/v and gate/up share a launch], called per projection"
+    else:
+        step = make_step(layers, world)
+        tp_mode = "nccl all_reduce after every row-parallel layer"
+        how = "tensor parallel"
+        if args.tp_mode == "peer":
+            # headline for N > 1: the peer-memory exchange; the NCCL variant is timed beside it
+            from torch_bnb_fp4_b200.parallel import PeerExchange
+            runner_n = GraphedCallable(step, [h0], warmup=3)
+            for _ in range(args.warmup):
+                runner_n.graph.replay()
+            dist.barrier(); torch.cuda.synchronize()
+            t_n = time_events(runner_n.graph.replay, args.steps)
+            v = torch.tensor([t_n], device=dev, dtype=torch.float64)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            nccl_line = {"tok_per_s": args.steps / float(v.item()), "ms_per_step": float(v.item()) / args.steps * 1e3}
+            ref_out = runner_n(h0).float().clone()
+            del runner_n
+            try:
+                exchange = PeerExchange(cfg["hidden"], torch.bfloat16, dev)
+                step_p = make_step_peer(layers, exchange)
+                with torch.no_grad():
+                    step_p(h0)  # shapes outside the streaming kernel raise here
+                ok = torch.ones(1, device=dev)
+            except Exception as e:  # noqa: BLE001
+                print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() > 0:
+                step = step_p
+                tp_mode = ("row-parallel partial sums exchanged through peer (symmetric) memory and summed in the "
+                           "consumer's x staging; q/k/v and gate/up grouped; one NCCL all_reduce per token for the "
+                           "final hidden state")
+            else:
+                nccl_line, exchange = None, None
+    launches_per_step = launches_of(lambda: step(h0))
     runner = GraphedCallable(step, [h0], warmup=max(3, args.warmup))
     if nccl_line is not None:
         got = runner(h0).float()
-        nccl_line["max_rel_diff_peer_vs_nccl"] = float((got - ref_out).abs().max() / ref_out.abs().max())
+        rel = float((got - ref_out).abs().max() / ref_out.abs().max())
+        nccl_line["max_rel_diff_peer_vs_nccl"] = rel
         exchange.check()
+        # a 32-layer bf16 chain summed in a different order: a few percent is rounding, more is a protocol error
+        assert rel <= 5e-2, f"peer-memory exchange disagrees with the NCCL path: {rel}"
     host_in = torch.randn(1, cfg["hidden"]).bfloat16().pin_memory()
     host_out = torch.empty(1, cfg["hidden"], dtype=torch.bfloat16).pin_memory()
 
@@ -388,56 +574,22 @@ def run_ours(args, rank, world):
         t_dev = time_events(runner.graph.replay, args.steps)
     barrier()
     t_dev = maxrank(t_dev)
+    if exchange is not None:
+        exchange.check()
 
-    # extension measured beside the headline: q/k/v and gate/up as grouped launches (128 launches per step)
+    # the same stack at the reference's granularity: one launch per linear (224 per token), no grouping
+    ungrouped = None
     if world == 1:
-        step_g = make_step_grouped(layers, world)
-        runner_g = GraphedCallable(step_g, [h0], warmup=3)
+        step_u = make_step(layers, 1)
+        n_u = launches_of(lambda: step_u(h0))
+        runner_u = GraphedCallable(step_u, [h0], warmup=3)
         for _ in range(args.warmup):
-            runner_g.graph.replay()
-        barrier()
-        t_grp = maxrank(time_events(runner_g.graph.replay, args.steps))
-        # the same through group_projections(): the UNMODIFIED per-projection step function, q/k/v and gate/up
-        # sharing launches behind the modules' backs
-        import torch_bnb_fp4
-
-        class _Block(torch.nn.Module):
-            def __init__(self, m):
-                super().__init__()
-                self.q_proj, self.k_proj, self.v_proj, self.o_proj = m["q"], m["k"], m["v"], m["o"]
-                self.gate_proj, self.up_proj, self.down_proj = m["gate"], m["up"], m["down"]
-
-        blocks = [_Block(m) for m in layers]
-        n_groups = sum(torch_bnb_fp4.group_projections(b) for b in blocks)
-
-        def step_dropin(h):
-            for b in blocks:
-                q = b.q_proj(h)
-                b.k_proj(h)
-                b.v_proj(h)
-                o = b.o_proj(q)
-                b.gate_proj(o)
-                up = b.up_proj(o)
-                h = b.down_proj(up)
-            return h
-
-        runner_d = GraphedCallable(step_dropin, [h0], warmup=3)
-        for _ in range(args.warmup):
-            runner_d.graph.replay()
-        t_drop = time_events(runner_d.graph.replay, args.steps)
-        with torch.no_grad():
-            for _ in range(2):
-                step_dropin(h0)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(10):
-                step_dropin(h0)
-            torch.cuda.synchronize()
-            t_drop_eager = (time.perf_counter() - t0) / 10
-        dropin = {"groups": n_groups, "tok_per_s": args.steps / t_drop, "eager_tok_per_s": 1.0 / t_drop_eager,
-                  "what": "group_projections(block) on blocks whose forward calls q/k/v/o/gate/up/down one by one"}
-    else:
-        t_grp, dropin = None, None
+            runner_u.graph.replay()
+        t_u = time_events(runner_u.graph.replay, args.steps)
+        ungrouped = {"value": nbytes * args.steps / t_u / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_u,
+                     "ms_per_step": t_u / args.steps * 1e3, "launches_per_step": n_u,
+                     "what": "one TorchFP4Linear launch per linear (group_projections_=False): the reference's granularity"}
+        del runner_u
 
     # end to end: pinned host input -> H2D -> replay -> D2H of the result, every step
     def e2e_step():
@@ -465,9 +617,14 @@ def run_ours(args, rank, world):
             host_out.copy_(step(hdev), non_blocking=True)
             torch.cuda.current_stream().synchronize()
         t_eager = maxrank(time.perf_counter() - t0) / n_eager
+    if exchange is not None:
+        exchange.check()
     if rank != 0:
         return
     peak, peak_kind = measured_peak()
+    if peak_kind != "measured":
+        print("[bench] MEASURED_PEAKS.json not found: roofline uses the FALLBACK peak of the profiling recipe",
+              file=sys.stderr)
     gbs = nbytes * args.steps / t_dev / 1e9
     line = {
         "metric": {"mistral7b": "batch-1 FP4 GEMV HBM GB/s (Mistral-7B-shape decode linear stack)",
@@ -475,17 +632,18 @@ def run_ours(args, rank, world):
                    "c1": "batch-1 FP4 GEMV HBM GB/s (4096x4096 layers)"}[args.workload],
         "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "tok_per_s": args.steps / t_dev,
         "config": {"workload": f"{args.workload}: {len(layers)} layers x 7 bnb-FP4 linears, blocksize 64, fp32 absmax, "
                                "batch 1, bf16 activations, random-init packed weights",
+                   "model_path": how,
                    "algorithmic_bytes_per_step": nbytes, "launches_per_step": launches_per_step,
                    "l2_policy": "inputs larger than L2 (weights stream once per step)",
                    "parallelism": f"tp{world}" if world > 1 else "single GPU",
                    "timing": "CUDA events around CUDA-graph replays"},
         "e2e": {"value": nbytes * args.steps / t_e2e / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_e2e,
                 "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2,
-                "mode": "GraphedCallable replay of TorchFP4Linear modules; pinned H2D + D2H + sync each step",
+                "mode": "GraphedCallable replay of the converted model; pinned H2D + D2H + sync each step",
                 "eager_tok_per_s": 1.0 / t_eager, "eager_value": nbytes / t_eager / 1e9},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak, "unit": "GB/s",
@@ -493,21 +651,27 @@ def run_ours(args, rank, world):
                      "kernel": "gemv_stream_kernel (fused dequant-GEMV, IMMA u8 x s8)",
                      "avg_launch_us": t_dev / args.steps / launches_per_step * 1e6,
                      "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step / world,
-                     "traffic": traffic_from_profile()},
+                     "traffic": traffic_from_profile() if world == 1 else None},
         "clocks": clk.summary(),
         "tp_collective": tp_mode,
-        "grouped_launches": None if t_grp is None else {"value": nbytes * args.steps / t_grp / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_grp,
-                             "ms_per_step": t_grp / args.steps * 1e3, "launches_per_step": len(layers) * 4,
-                             "frac_of_peak": nbytes * args.steps / t_grp / 1e9 / world / peak,
-                             "what": "extension: q/k/v and gate/up each issued as one fp4_b200_gemv_grouped launch "
-                                     "(TorchFP4LinearGroup); same arithmetic up to fp32 summation order, 4 instead of 7 launches per layer",
-                             "dropin": dropin},
+        "ungrouped_launches": ungrouped,
     }
     if nccl_line is not None:
         nccl_line["value"] = nbytes / (nccl_line["ms_per_step"] * 1e-3) / 1e9
         line["nccl_allreduce_variant"] = nccl_line
+    if world == 1 and not args.no_extras:
+        del runner, layers, bnb_layers, step
+        if "model" in locals():
+            del model
+        torch.cuda.empty_cache()
+        for key, fn in (("c1_single_layer", extra_c1), ("sanity_mlp", extra_sanity_mlp), ("gemm_sweep", extra_gemm_sweep)):
+            try:
+                line[key] = fn(dev)
+            except Exception as e:  # noqa: BLE001 - an extra must never cost the headline
+                line[key] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args.cpu_seconds)
+    ClockSampler.stop()
     emit(json.dumps(line))
 
 
@@ -570,6 +734,8 @@ def run_reference(args, rank, world):
     for _ in range(max(1, args.warmup)):
         step(h0)
     torch.cuda.synchronize()
+    ClockSampler.start(0)
+    time.sleep(0.3)
     with ClockSampler(0) as clk:
         t_dev = time_events(lambda: step(h0), args.steps)
 
@@ -593,6 +759,7 @@ def run_reference(args, rank, world):
                                   "arm runs its CUDA extension on the GPU (see DESIGN.md)"},
                  "e2e": {"value": nbytes * args.steps / t_e2e / 1e9, "unit": "GB/s", "tok_per_s": args.steps / t_e2e,
                          "h2d_bytes_per_step": host_in.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2}})
+    ClockSampler.stop()
     emit(json.dumps(base))
 
 
@@ -604,6 +771,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mistral7b", choices=["mistral7b", "c1", "llama70b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config #1 / #2 / #5 extra keys")
     ap.add_argument("--tp-mode", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory exchange fused into the consumer launch (default) or NCCL all_reduce")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

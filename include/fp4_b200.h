@@ -109,6 +109,8 @@ typedef struct {
 } fp4_b200_tp_t;
 
 int fp4_b200_abi_version(void);
+/* number of kernels this library has launched in this process (diagnostics / benchmark bookkeeping) */
+unsigned long long fp4_b200_launch_count(void);
 const char* fp4_b200_status_string(int status);
 
 /* Blockwise dequantise n elements:  out[i] = RN_T(fp32_mul(code[nib_i], absmax[i / blocksize])).

@@ -291,6 +291,29 @@ def test_gemv_nested_absmax_in_kernel(cuda):
         assert normwise(y.float().cpu().numpy(), exact) <= TOL64[torch.bfloat16]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,K,batch", [(1024, 4096, 1), (2048, 1024, 3), (4096, 768, 2), (768, 14336, 1), (1536, 2048, 6)])
+def test_gemv_nested_streaming_kernel(cuda, dtype, N, K, batch):
+    """The double-quantised absmax is decoded INSIDE the streaming GEMV (uint8 codes + absmax2 ride in the ring
+    slot; two separately rounded fp32 ops): the result must be bit-identical to the same kernel fed the
+    materialised fp32 absmax (same arithmetic, 0.516 instead of 0.5625 bytes per weight)."""
+    packed, am_true, _ = synth_quant(N * K, 64, seed=N % 89)
+    code2 = bnb_compat.create_dynamic_map()
+    off = float(am_true.mean())
+    q, am2 = bnb_compat.quantize_blockwise_8bit(torch.from_numpy(am_true - off), code2, 256)
+    absmax = oracle.denest(q.numpy(), code2.numpy(), am2.numpy(), off, 256)
+    nested = ext.make_nested(q.to(cuda), code2.to(cuda), am2.to(cuda), off, 256)
+    x = torch.randn(batch, K, generator=torch.Generator().manual_seed(K % 97)).to(dtype).to(cuda)
+    A = to_dev(packed, cuda).view(-1, 1)
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(5)) * 0.1).to(dtype).to(cuda)
+    y_n = ext.gemv_fp4_bias(x, A, None, _code(cuda), 64, ST[dtype], [N, K], bias, nested, 0)
+    y_f = ext.gemv_fp4_bias(x, A, to_dev(absmax, cuda), _code(cuda), 64, ST[dtype], [N, K], bias, None, 0)
+    assert np.array_equal(bits_of(y_n), bits_of(y_f))
+    exact = oracle.linear_f64(x.float().cpu().numpy(), packed, absmax, oracle.bnb_code(), bias.float().cpu().numpy(),
+                              N, K, 64)
+    assert normwise(y_n.float().cpu().numpy(), exact) <= TOL64[dtype]
+
+
 def test_gemv_rejects_bad_arguments(cuda):
     packed, absmax, _ = synth_quant(64 * 64, 64, seed=1)
     A, am, code = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda), _code(cuda)

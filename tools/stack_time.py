@@ -28,8 +28,12 @@ def main():
     layers, nbytes = bench.build_stack(cfg, dev)
     h0 = torch.randn(1, cfg["hidden"], device=dev).bfloat16()
     env = " ".join(f"{k[13:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("FP4_B200_GEMV_"))
-    for mode, mk in (("ungrouped", bench.make_step), ("grouped", bench.make_step_grouped)):
-        r = GraphedCallable(mk(layers, 1), [h0], warmup=3)
+    import torch_bnb_fp4
+    blocks = [bench.Block(dict(m)) for m in layers]
+    for b in blocks:
+        torch_bnb_fp4.group_projections(b)
+    for mode, stepfn in (("ungrouped", bench.make_step(layers, 1)), ("grouped", bench.make_step_blocks(blocks))):
+        r = GraphedCallable(stepfn, [h0], warmup=3)
         for _ in range(5):
             r.graph.replay()
         best = 1e9

@@ -21,7 +21,7 @@ EXPORTS = [
     "fp4_b200_dequantize_nested", "fp4_b200_absmax_denest", "fp4_b200_gemv",
     "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
     "fp4_b200_quantize", "fp4_b200_layer_create", "fp4_b200_layer_gemv", "fp4_b200_layer_destroy",
-    "fp4_b200_layer_create_grouped", "fp4_b200_layer_gemv_grouped",
+    "fp4_b200_layer_create_grouped", "fp4_b200_layer_gemv_grouped", "fp4_b200_launch_count",
 ]
 
 
@@ -72,10 +72,11 @@ def _load() -> ctypes.CDLL:
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the ABI is incomplete
         if name not in ("fp4_b200_status_string", "fp4_b200_gemv_workspace_bytes", "fp4_b200_layer_create",
-                        "fp4_b200_layer_create_grouped", "fp4_b200_layer_destroy"):
+                        "fp4_b200_layer_create_grouped", "fp4_b200_layer_destroy", "fp4_b200_launch_count"):
             getattr(lib, name).restype = i32
     lib.fp4_b200_gemv_workspace_bytes.restype = ctypes.c_size_t
     lib.fp4_b200_layer_create.restype = vp
+    lib.fp4_b200_launch_count.restype = ctypes.c_ulonglong
     lib.fp4_b200_layer_create_grouped.restype = vp
     lib.fp4_b200_layer_destroy.restype = None
     if lib.fp4_b200_abi_version() != 1:

@@ -19,7 +19,10 @@ def module_path() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    from . import build as core
+    import importlib.util  # (loaded by path: importing the package needs the library this builds)
+    spec = importlib.util.spec_from_file_location("fp4_b200_build", os.path.join(HERE, "build.py"))
+    core = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(core)
     core.build()
     out = module_path()
     deps = [SRC, os.path.join(HERE, "..", "include", "fp4_b200.h")]

@@ -1,5 +1,6 @@
 // extern "C" surface of libfp4_b200.so (declared in include/fp4_b200.h): argument validation and
 // kernel selection only; the kernels live in dequant.cu, gemv_generic.cu, gemv_imma.cu, gemm_tcgen05.cu.
+#include <atomic>
 #include <new>
 
 #include "common.cuh"
@@ -27,8 +28,8 @@ int gemv_i8_dispatch(const void*, const uint8_t*, const float*, const void*, voi
                      int, int, int, cudaStream_t);
 bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested,
                            const void* packed, const void* absmax);
-int gemv_stream_dispatch(const void*, const uint8_t*, const float*, const void*, void*, int, int, int, int,
-                         cudaStream_t);
+int gemv_stream_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*, const void*, void*, int,
+                         int, int, int, cudaStream_t);
 bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int blocksize, int dtype,
                                  const uint8_t* const* packed, const float* const* absmax);
 int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
@@ -40,7 +41,17 @@ int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float
 
 using namespace fp4b200;
 
+// kernels launched by this library in this process (every entry point below launches exactly one kernel when it
+// returns 0): lets a benchmark report its launch count from the library's own bookkeeping
+static std::atomic<unsigned long long> g_launches{0};
+static inline int counted(int rc) {
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+}
+
 extern "C" {
+
+unsigned long long fp4_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int fp4_b200_abi_version(void) { return FP4_B200_ABI_VERSION; }
 
@@ -62,21 +73,21 @@ const char* fp4_b200_status_string(int s) {
 int fp4_b200_dequantize(const uint8_t* packed, const float* absmax, const float* code, void* out,
                         int64_t n, int blocksize, int out_dtype, void* stream) {
     if (!absmax) return FP4_B200_ERR_NULL;
-    return dequant_dispatch(packed, absmax, nullptr, code, out, n, blocksize, out_dtype,
-                            (cudaStream_t)stream);
+    return counted(dequant_dispatch(packed, absmax, nullptr, code, out, n, blocksize, out_dtype,
+                            (cudaStream_t)stream));
 }
 
 int fp4_b200_dequantize_nested(const uint8_t* packed, const fp4_b200_nested_t* nested,
                                const float* code, void* out, int64_t n, int blocksize,
                                int out_dtype, void* stream) {
     if (!nested) return FP4_B200_ERR_NULL;
-    return dequant_dispatch(packed, nullptr, nested, code, out, n, blocksize, out_dtype,
-                            (cudaStream_t)stream);
+    return counted(dequant_dispatch(packed, nullptr, nested, code, out, n, blocksize, out_dtype,
+                            (cudaStream_t)stream));
 }
 
 int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, int64_t nblocks,
                            void* stream) {
-    return denest_dispatch(nested, absmax_out, nblocks, (cudaStream_t)stream);
+    return counted(denest_dispatch(nested, absmax_out, nblocks, (cudaStream_t)stream));
 }
 
 int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
@@ -110,25 +121,26 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
         if (workspace_bytes < gemv_imma_workspace_bytes(N)) return FP4_B200_ERR_WORKSPACE;
         // default: L2-prefetched register-streamed integer tensor-core kernel (whole row tiles per CTA)
         if (!(flags & FP4_B200_FLAG_NO_STREAM) &&
-            gemv_stream_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
-            return gemv_stream_dispatch(x, packed, absmax, bias, out, batch, N, K, dtype,
-                                        (cudaStream_t)stream);
+            gemv_stream_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed,
+                                  nested ? (const void*)nested->qabsmax : (const void*)absmax))
+            return counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, batch, N, K, dtype,
+                                        (cudaStream_t)stream));
         // stream-K integer tensor-core kernel (TMA-staged) where its layout requirements hold
         if (!(flags & FP4_B200_FLAG_NO_I8) &&
             gemv_i8_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
-            return gemv_i8_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch, N,
-                                    K, dtype, (cudaStream_t)stream);
+            return counted(gemv_i8_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch, N,
+                                    K, dtype, (cudaStream_t)stream));
         // fp16 tensor-core kernels: TMA-staged, else register-streamed (nested absmax, other block sizes)
         if (!(flags & FP4_B200_FLAG_NO_TMA) &&
             gemv_tma_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
-            return gemv_tma_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch,
-                                     N, K, dtype, (cudaStream_t)stream);
-        return gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, workspace,
+            return counted(gemv_tma_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch,
+                                     N, K, dtype, (cudaStream_t)stream));
+        return counted(gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, workspace,
                                   workspace_bytes, batch, N, K, bs_log2, dtype,
-                                  (cudaStream_t)stream);
+                                  (cudaStream_t)stream));
     }
-    return gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
-                                 bs_log2, dtype, (cudaStream_t)stream);
+    return counted(gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
+                                 bs_log2, dtype, (cudaStream_t)stream));
 }
 
 int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
@@ -155,8 +167,8 @@ int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* pack
     }
     if (!gemv_stream_group_supported(nmat, batch, N, K, blocksize, dtype, packed, absmax))
         return FP4_B200_ERR_UNSUPPORTED;
-    return gemv_stream_group_dispatch(x, nmat, packed, absmax, bias, out, N, batch, K, dtype, tp,
-                                      (cudaStream_t)stream);
+    return counted(gemv_stream_group_dispatch(x, nmat, packed, absmax, bias, out, N, batch, K, dtype, tp,
+                                      (cudaStream_t)stream));
 }
 
 int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
@@ -229,13 +241,13 @@ int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, con
     if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16) return FP4_B200_ERR_DTYPE;
     if (ilog2_exact(blocksize) < 0) return FP4_B200_ERR_BLOCKSIZE;
     if (M == 0 || N == 0) return FP4_B200_OK;
-    return gemm_tcgen05_dispatch(x, packed, absmax, code, bias, out, M, N, K, blocksize, dtype,
-                                 flags, (cudaStream_t)stream);
+    return counted(gemm_tcgen05_dispatch(x, packed, absmax, code, bias, out, M, N, K, blocksize, dtype,
+                                 flags, (cudaStream_t)stream));
 }
 
 int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
                       float* absmax, void* stream) {
-    return quantize_dispatch(w, dtype, n, blocksize, packed, absmax, (cudaStream_t)stream);
+    return counted(quantize_dispatch(w, dtype, n, blocksize, packed, absmax, (cudaStream_t)stream));
 }
 
 }  // extern "C"

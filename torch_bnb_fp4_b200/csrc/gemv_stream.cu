@@ -88,6 +88,15 @@ struct Params {
     const void* vbias[kMaxGroup];  // may be NULL
     void* vout[kMaxGroup];
     int Nm[kMaxGroup];             // out_features of matrix m (row pitch of its output)
+    // nested (double-quantised) absmax of matrix m, decoded in the kernel: uint8 codes in place of the
+    // fp32 absmax (vqabs rebased to global rows like vabsmax), the 256-entry map, fp32 absmax2 per 2^bs2_log2
+    // blocks (indexed by the matrix's own block number) and the offset.  nested_mask bit m: matrix m is nested.
+    const uint8_t* vqabs[kMaxGroup];
+    const float* vcode2[kMaxGroup];
+    const float* vabs2[kMaxGroup];
+    float voffset[kMaxGroup];
+    int vbs2_log2[kMaxGroup];
+    uint32_t nested_mask;
     uint32_t tstart[kMaxGroup];    // first global tile of matrix m (tstart[0] = 0; unused entries = UINT32_MAX)
     int batch, K;
     uint32_t upt;     // units per row tile = ceil(K / 512)
@@ -145,6 +154,9 @@ __device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_ca16(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_pending(uint32_t pending) {  // uniform across the CTA
@@ -242,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     uint8_t* sZero = sX + (size_t)nq * XP;                // kZeroBytes of zeros
     float* sXs = reinterpret_cast<float*>(sZero + kZeroBytes);  // [batch][nkb] 2^-e / 192
     float* sPart = sXs + (size_t)batch * nkb;             // [kW][2][batch*16]
+    float* sCode2 = sPart + (size_t)kW * 2 * batch * 16;  // [kMaxGroup][256], nested absmax only
 
     // ---- this CTA's tiles and this warp's units ----------------------------------------------------
     const uint32_t cta = blockIdx.x;
@@ -262,12 +275,21 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     const uint32_t row8 = 8 * rowb;
     const uint8_t* wp;
     const float* ap;  // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds row g + 8 (t & 1), blocks 4 (t >> 1) ..
+    const uint8_t* qp = nullptr;  // nested: this lane's four uint8 codes ...
+    const float* a2p = nullptr;   // ... and the absmax2 of their 256-group (four aligned blocks share one)
+    bool ld_nested = false;
     uint32_t ld_gt = tile0 + tl_a;
     auto loader_at = [&](uint32_t gt, uint32_t kunit) {
         const int m = mat_of(gt);
         const size_t trow = (size_t)gt * 16;
         wp = p.vpacked[m] + (trow + g) * rowb + kunit * 256 + t * 16;
         ap = p.vabsmax[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
+        ld_nested = (p.nested_mask >> m) & 1u;
+        if (ld_nested) {
+            qp = p.vqabs[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
+            const size_t lblk = ((size_t)(gt - p.tstart[m]) * 16 + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
+            a2p = p.vabs2[m] + (lblk >> p.vbs2_log2[m]);
+        }
     };
     loader_at(ld_gt, ku_a);
     TL_STAMP(0);
@@ -286,7 +308,14 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 cp_async_cg16(dst + j * 1024 + 512, wp + j * 64 + row8);
             }
         }
-        if (j0 == 0 && 2 * (t >> 1) < nst) cp_async_ca16(dst - ring_a + ring_am, ap);  // this lane's 4 blocks exist
+        if (j0 == 0 && 2 * (t >> 1) < nst) {  // this lane's 4 blocks exist
+            if (ld_nested) {  // four codes + the absmax2 of their group ride in the slot (decoded when consumed)
+                cp_async_ca4(dst - ring_a + ring_am, qp);
+                cp_async_ca4(dst - ring_a + ring_am + 4, a2p);
+            } else {
+                cp_async_ca16(dst - ring_a + ring_am, ap);
+            }
+        }
         if (j1 < 4) return;
         if (++ld_ku == p.upt) {
             ld_ku = 0;
@@ -294,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         } else {
             wp += 256;
             ap += 8;
+            if (ld_nested) loader_at(ld_gt, ld_ku);  // (the 256-group of the codes may change)
         }
         ++issued;
     };
@@ -328,6 +358,12 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 
     // ---- 2. stage x as s8 residual terms, one power-of-two scale per (batch row, 64-block) ----------
     for (uint32_t i = tid; i < kZeroBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sZero)[i] = 0u;
+    if (p.nested_mask) {
+        for (uint32_t i = tid; i < kMaxGroup * 256; i += kThreads) {
+            const uint32_t m = i >> 8;
+            if ((p.nested_mask >> m) & 1u) sCode2[i] = __ldg(p.vcode2[m] + (i & 255u));
+        }
+    }
     {
         const T* x = reinterpret_cast<const T*>(p.x);
         const int nchunk = (int)(K >> 3);
@@ -566,7 +602,20 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 #endif
         const uint32_t sl = ring_a + slot * kSlot;
         if constexpr (ALIGNED) __syncwarp();  // the lanes read each other's copies
-        const uint4 amc = lds_u4(ring_am + slot * kSlot);
+        uint4 amc = lds_u4(ring_am + slot * kSlot);
+        if (p.nested_mask) {  // uniform
+            const int mm = mat_of(tile0 + tl);
+            if ((p.nested_mask >> mm) & 1u) {
+                // absmax = fp32_add(fp32_mul(code2[q], absmax2), offset): two separately rounded operations
+                const uint32_t codes = amc.x;
+                const float a2 = __uint_as_float(amc.y), off = p.voffset[mm];
+                const float* tab = sCode2 + mm * 256;
+                amc.x = __float_as_uint(__fadd_rn(__fmul_rn(tab[codes & 255u], a2), off));
+                amc.y = __float_as_uint(__fadd_rn(__fmul_rn(tab[(codes >> 8) & 255u], a2), off));
+                amc.z = __float_as_uint(__fadd_rn(__fmul_rn(tab[(codes >> 16) & 255u], a2), off));
+                amc.w = __float_as_uint(__fadd_rn(__fmul_rn(tab[codes >> 24], a2), off));
+            }
+        }
         uint32_t xa[NCT], sa[NCT];
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
@@ -763,7 +812,8 @@ static bool use_aligned(int batch, int nt) {
 static int column_tiles(int batch, int nt) { return (batch * nt * (use_aligned(batch, nt) ? 1 : 2) + 7) / 8; }
 
 static size_t fixed_smem_bytes(int batch, int K, int nt) {
-    return (size_t)batch * nt * (K + (use_aligned(batch, nt) ? 16 : 0)) + kZeroBytes + (size_t)batch * (K / 64) * 4 + (size_t)kW * 2 * batch * 16 * 4;
+    return (size_t)batch * nt * (K + (use_aligned(batch, nt) ? 16 : 0)) + kZeroBytes + (size_t)batch * (K / 64) * 4 +
+           (size_t)kW * 2 * batch * 16 * 4 + (size_t)kMaxGroup * 256 * 4 /* nested code2 tables */;
 }
 
 struct Group {
@@ -771,6 +821,7 @@ struct Group {
     int nmat;
     const uint8_t* packed[kMaxGroup];
     const float* absmax[kMaxGroup];
+    const fp4_b200_nested_t* nested[kMaxGroup];  // non-NULL: absmax[m] is ignored
     const void* bias[kMaxGroup];
     void* out[kMaxGroup];
     int N[kMaxGroup];
@@ -820,6 +871,10 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     p.x = x;
     p.batch = batch; p.K = K;
     if (gr.tp) p.tp = *gr.tp; else { p.tp = fp4_b200_tp_t(); }
+    p.nested_mask = 0;
+    for (int m = 0; m < kMaxGroup; ++m) {
+        p.vqabs[m] = nullptr; p.vcode2[m] = nullptr; p.vabs2[m] = nullptr; p.voffset[m] = 0.f; p.vbs2_log2[m] = 0;
+    }
     uint32_t tiles = 0;
     for (int m = 0; m < kMaxGroup; ++m) {
         if (m < gr.nmat) {
@@ -827,7 +882,15 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
             const size_t grow0 = (size_t)tiles * 16;
             p.tstart[m] = tiles;
             p.vpacked[m] = gr.packed[m] - grow0 * ((size_t)K / 2);
-            p.vabsmax[m] = gr.absmax[m] - grow0 * ((size_t)K / 64);
+            p.vabsmax[m] = gr.absmax[m] ? gr.absmax[m] - grow0 * ((size_t)K / 64) : nullptr;
+            if (gr.nested[m]) {
+                const fp4_b200_nested_t& nd = *gr.nested[m];
+                p.nested_mask |= 1u << m;
+                p.vqabs[m] = nd.qabsmax - grow0 * ((size_t)K / 64);
+                p.vcode2[m] = nd.code2; p.vabs2[m] = nd.absmax2; p.voffset[m] = nd.offset;
+                p.vbs2_log2[m] = ilog2_exact(nd.blocksize2);
+                p.vabsmax[m] = reinterpret_cast<const float*>(p.vqabs[m]);  // never dereferenced
+            }
             p.vbias[m] = gr.bias[m] ? reinterpret_cast<const uint8_t*>(gr.bias[m]) - grow0 * sizeof(T) : nullptr;
             p.vout[m] = reinterpret_cast<uint8_t*>(gr.out[m]) - grow0 * sizeof(T);
             p.Nm[m] = gr.N[m];
@@ -902,7 +965,8 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
                            const void* absmax) {
     static const int disabled = env_int("FP4_B200_GEMV_NO_STREAM", 0);
     static const int min_tiles = env_int("FP4_B200_GEMV_STREAM_MIN_TILES", 48);
-    if (disabled || nested || blocksize != 64) return false;
+    (void)nested;  // decoded in the kernel
+    if (disabled || blocksize != 64) return false;
     if (batch < 1 || batch > 8 || N <= 0 || K <= 0) return false;
     if (K % 256 != 0 || N % 16 != 0) return false;
     if (N / 16 < min_tiles) return false;  // too few row tiles to occupy the GPU: the stream-K kernels split K
@@ -913,11 +977,17 @@ bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bo
     return fixed_smem_bytes(batch, K, nt) + (size_t)kW * kSlot <= kMaxSmem;
 }
 
-int gemv_stream_dispatch(const void* x, const uint8_t* packed, const float* absmax, const void* bias, void* out,
-                         int batch, int N, int K, int dtype, cudaStream_t st) {
+static bool nested_ok(const fp4_b200_nested_t* nd) {
+    return !nd || (nd->qabsmax && nd->code2 && nd->absmax2 && ilog2_exact(nd->blocksize2) >= 2 &&
+                   reinterpret_cast<uintptr_t>(nd->qabsmax) % 4 == 0);
+}
+
+int gemv_stream_dispatch(const void* x, const uint8_t* packed, const float* absmax, const fp4_b200_nested_t* nested,
+                         const void* bias, void* out, int batch, int N, int K, int dtype, cudaStream_t st) {
     Group gr = {};
     gr.nmat = 1;
-    gr.packed[0] = packed; gr.absmax[0] = absmax; gr.bias[0] = bias; gr.out[0] = out; gr.N[0] = N;
+    gr.packed[0] = packed; gr.absmax[0] = absmax; gr.nested[0] = nested; gr.bias[0] = bias; gr.out[0] = out; gr.N[0] = N;
+    if (!nested_ok(nested)) return FP4_B200_ERR_UNSUPPORTED;
     return dispatch_group(x, gr, batch, K, dtype, st);
 }
 
