@@ -53,10 +53,11 @@ def to_bnb(model, dtype):
             new = bnb_compat.Linear4bit(child.in_features, child.out_features, bias=child.bias is not None,
                                         compute_dtype=dtype, compress_statistics=False, quant_type="fp4")
             new.weight = bnb_compat.Params4bit(child.weight.data.clone(), requires_grad=False,
-                                               compress_statistics=False, quant_type="fp4")
+                                               compress_statistics=False, quant_type="fp4").cuda(0)  # quantises
+            assert new.weight.data.dtype == torch.uint8 and new.weight.quant_state is not None
             if child.bias is not None:
                 new.bias = nn.Parameter(child.bias.data.clone(), requires_grad=False)
-            model._modules[name] = new.cuda()
+            model._modules[name] = new
         else:
             to_bnb(child, dtype)
     return model

@@ -314,6 +314,40 @@ def test_gemv_nested_streaming_kernel(cuda, dtype, N, K, batch):
     assert normwise(y_n.float().cpu().numpy(), exact) <= TOL64[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemv_batch_sweep_has_no_cliff(cuda, dtype):
+    """Every batch 1..8 of the raw gemv_fp4 op (the C-ABI, not the module dispatcher) on decode-sized layers runs
+    on the streaming kernel - where the integer terms of x do not fit shared memory the call is split into two
+    launches - and is correct.  Floor: no case below 10 % of the measured HBM bandwidth on the large layers
+    (round 1: fp32 batch 7-8 on 28672x8192 fell through to the generic kernel at 1.3 %)."""
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    code = _code(cuda)
+    for N, K, floor in ((4096, 4096, 0.04), (14336, 4096, 0.10), (28672, 8192, 0.10)):
+        packed = torch.randint(0, 256, (N * K // 2, 1), dtype=torch.uint8, device=cuda, generator=gen)
+        absmax = torch.rand(N * K // 64, device=cuda, generator=gen) * 0.02 + 0.01
+        w = ext.dequantize_fp4(packed, absmax, 64, N, K, ext.float32)
+        for batch in range(1, 9):
+            x = torch.randn(batch, K, device=cuda, generator=gen).to(dtype)
+            y = ext.gemv_fp4(x, packed, absmax, code, 64, ST[dtype], [N, K])
+            if batch in (1, 5, 8):
+                ref = x.double() @ w.double().t()
+                err = float((y.double() - ref).abs().max() / ref.abs().max())
+                assert err <= TOL64[dtype], (N, K, batch, err)
+            for _ in range(3):
+                ext.gemv_fp4(x, packed, absmax, code, 64, ST[dtype], [N, K])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                ext.gemv_fp4(x, packed, absmax, code, 64, ST[dtype], [N, K])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 100.0
+            gbs = (N * K * 0.5625) / us / 1e3
+            assert gbs >= floor * 6557.0, (N, K, batch, dtype, us, gbs)
+        del packed, absmax, w
+
+
 def test_gemv_rejects_bad_arguments(cuda):
     packed, absmax, _ = synth_quant(64 * 64, 64, seed=1)
     A, am, code = to_dev(packed, cuda).view(-1, 1), to_dev(absmax, cuda), _code(cuda)

@@ -37,6 +37,7 @@ T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
 GEMV_X_SMEM_BYTES = 150 * 1024  # x terms the streaming GEMV can stage next to one ring slot per warp
+GEMV_TWICE_MAX_WEIGHTS = 32 * 1024 * 1024  # 9..16 rows: layers up to this many weights take two 8-row GEMVs
 GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
 GEMM_MAX_ROWS = 512     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
 
@@ -242,14 +243,23 @@ class QuantData:
             # the streaming GEMV keeps x (as integer terms) in shared memory: rows * K * 2 bytes for 16-bit
             # inputs.  Where that does not fit (e.g. 8 rows x K = 14336) the tensor-core GEMM with a 16-token tile
             # is several times faster than the stream-K fallback
-            # (fp32 inputs take four integer terms per element instead of two and have no fused GEMM: dequant +
-            # cuBLAS then, the generic GEMV is an order of magnitude slower at that size)
+            # (fp32 inputs take four integer terms per element instead of two and have no fused GEMM: the C-ABI then
+            # runs the GEMV as two launches of half the rows each)
             x_bytes = rows * k * (4 if A.dtype == torch.float32 else 2)
             too_big = rows > 2 and x_bytes > GEMV_X_SMEM_BYTES
-            if not (too_big and (gemm_ok or A.dtype == torch.float32)):
+            if not (too_big and gemm_ok):
                 if not A.is_contiguous():
                     A = A.contiguous()
                 return self._qgemv(A)
+        if (GEMV_MAX_BATCH < rows <= 2 * GEMV_MAX_BATCH and self.numel <= GEMV_TWICE_MAX_WEIGHTS
+                and k % 32 == 0 and self.blocksize % 32 == 0 and self._code_is_std):
+            # 9..16 rows on a small layer: the GEMM's few weight tiles leave most SMs idle and its one dequantiser
+            # warp per sub-partition sets the pace (16 us on 2048x2048); two 8-row GEMVs are faster there
+            A2 = A.reshape(rows, k)
+            if not A2.is_contiguous():
+                A2 = A2.contiguous()
+            y = torch.cat([self._qgemv(A2[:GEMV_MAX_BATCH]), self._qgemv(A2[GEMV_MAX_BATCH:])], dim=0)
+            return y.view(A.shape[:-1] + (self.M,))
         if rows <= GEMM_MAX_ROWS and gemm_ok:
             if not A.is_contiguous():
                 A = A.contiguous()

@@ -125,6 +125,23 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                                   nested ? (const void*)nested->qabsmax : (const void*)absmax))
             return counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, batch, N, K, dtype,
                                         (cudaStream_t)stream));
+        // the rows of x (as integer terms) that do not fit the streaming kernel's shared memory together - fp32
+        // inputs with batch 5..8 on K = 8192, 16-bit batch 8 on K = 14336 ... - are done in two launches: the
+        // weights stream twice, which is still an order of magnitude faster than the kernels below
+        if (batch >= 2 && !(flags & FP4_B200_FLAG_NO_STREAM)) {
+            const int b0 = (batch + 1) / 2, b1 = batch - b0;
+            const void* aq = nested ? (const void*)nested->qabsmax : (const void*)absmax;
+            if (gemv_stream_supported(b0, N, K, blocksize, dtype, nested != nullptr, packed, aq)) {
+                const size_t es = dtype == FP4_B200_F32 ? 4 : 2;
+                int rc = counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, b0, N, K, dtype,
+                                                      (cudaStream_t)stream));
+                if (rc) return rc;
+                return counted(gemv_stream_dispatch(static_cast<const uint8_t*>(x) + (size_t)b0 * K * es, packed,
+                                                    absmax, nested, bias,
+                                                    static_cast<uint8_t*>(out) + (size_t)b0 * N * es, b1, N, K,
+                                                    dtype, (cudaStream_t)stream));
+            }
+        }
         // stream-K integer tensor-core kernel (TMA-staged) where its layout requirements hold
         if (!(flags & FP4_B200_FLAG_NO_I8) &&
             gemv_i8_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
