@@ -201,6 +201,22 @@ int fp4_b200_gemm(const void* x, const uint8_t* packed, const float* absmax, con
 int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed,
                       float* absmax, void* stream);
 
+/* Fused neighbours of the Linear: what the reference runs as separate elementwise kernels
+ * after its gemv_fp4 calls (torch_bnb_fp4/__init__.py:608-613 adds even the bias as a second op).
+ *   gate_act != 0 (1 = SiLU, 2 = GELU tanh approximation): the call has nmat == 2 matrices of the same N - the gate
+ *     and the up projection of a gated MLP - and writes ONE output, out[0][b, r] =
+ *     act(x W_gate^T + bias_gate)[b, r] * (x W_up^T + bias_up)[b, r]; out[1] is ignored.  N % 8 == 0.
+ *   residual: NULL, or a HOST array of nmat device pointers (entries may be NULL) to [batch, N_m] tensors of the
+ *     call's dtype that are added to out[m] (the residual stream around an o / down projection). */
+typedef struct {
+    int gate_act;
+    const void* const* residual;
+} fp4_b200_epilogue_t;
+int fp4_b200_gemv_grouped_ex(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                             const void* const* bias, void* const* out, const int* N, int batch, int K,
+                             int blocksize, int dtype, unsigned flags, const fp4_b200_tp_t* tp,
+                             const fp4_b200_epilogue_t* epilogue, void* stream);
+
 /* fp4_b200_gemv_grouped with the tensor-parallel exchange described by fp4_b200_tp_t; tp may be NULL (plain).
  * x may be NULL when tp->in_world > 1 (x is then the sum of the ranks' partials). */
 int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,

@@ -201,3 +201,84 @@ def test_tp_shards_cut_at_load(cuda, nested):
     assert normwise(torch.cat(cols, dim=-1).float().cpu().numpy(), y_full.cpu().numpy()) <= 8e-3
     y_row = sum(rows)
     assert normwise(y_row.cpu().numpy(), y_full.cpu().numpy()) <= 1e-2
+
+
+# ---------------------------------------------------------------- fused neighbours of the Linear
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("rows", [1, 2, 5, 8])
+@pytest.mark.parametrize("act", ["silu", "gelu_tanh"])
+def test_gated_mlp_epilogue_matches_oracle(cuda, dtype, rows, act):
+    """gate/up in one launch with act(gate) * up in the epilogue: against the fp64 oracle linear + fp64 activation."""
+    H, I = 1024, 2816
+    rng = np.random.default_rng(rows)
+    pg, ag = oracle.quantize((rng.standard_normal(I * H) * 0.03).astype(np.float32), 64)
+    pu, au = oracle.quantize((rng.standard_normal(I * H) * 0.03).astype(np.float32), 64)
+    x = to_dev(rng.standard_normal((rows, H)).astype(np.float32), cuda, dtype)
+    bg = to_dev(rng.standard_normal(I).astype(np.float32) * 0.1, cuda, dtype)
+    st = {torch.float16: ext.float16, torch.bfloat16: ext.bfloat16, torch.float32: ext.float32}[dtype]
+    outs = ext.gemv_fp4_fused(x, [to_dev(pg, cuda).view(-1, 1), to_dev(pu, cuda).view(-1, 1)],
+                              [to_dev(ag, cuda), to_dev(au, cuda)], 64, st, [[I, H], [I, H]], [bg, None], gate_act=act)
+    assert outs is not None and len(outs) == 1 and outs[0].shape == (rows, I) and outs[0].dtype == dtype
+    xr = x.float().cpu().numpy()
+    code = oracle.bnb_code()
+    g = oracle.linear_f64(xr, pg, ag, code, bg.float().cpu().numpy(), I, H, 64)
+    u = oracle.linear_f64(xr, pu, au, code, None, I, H, 64)
+    if act == "silu":
+        a = g / (1.0 + np.exp(-g))
+    else:
+        a = 0.5 * g * (1.0 + np.tanh(0.7978845608028654 * (g + 0.044715 * g ** 3)))
+    tol = 2e-5 if dtype == torch.float32 else (6e-3 if dtype == torch.bfloat16 else 1.5e-3)
+    assert normwise(outs[0].float().cpu().numpy(), a * u) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows", [1, 4, 8])
+def test_residual_epilogue_matches_oracle(cuda, dtype, rows):
+    N, K = 1024, 2816
+    rng = np.random.default_rng(7 + rows)
+    p, a = oracle.quantize((rng.standard_normal(N * K) * 0.03).astype(np.float32), 64)
+    x = to_dev(rng.standard_normal((rows, K)).astype(np.float32), cuda, dtype)
+    res = to_dev(rng.standard_normal((rows, N)).astype(np.float32), cuda, dtype)
+    bias = to_dev(rng.standard_normal(N).astype(np.float32) * 0.1, cuda, dtype)
+    st = {torch.bfloat16: ext.bfloat16, torch.float32: ext.float32}[dtype]
+    outs = ext.gemv_fp4_fused(x, [to_dev(p, cuda).view(-1, 1)], [to_dev(a, cuda)], 64, st, [[N, K]], [bias],
+                              residuals=[res])
+    exact = oracle.linear_f64(x.float().cpu().numpy(), p, a, oracle.bnb_code(), bias.float().cpu().numpy(), N, K, 64)
+    exact = exact + res.float().cpu().numpy()
+    assert normwise(outs[0].float().cpu().numpy(), exact) <= (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+class _HFMLP(nn.Module):  # the forward of transformers' MistralMLP / LlamaMLP
+    def __init__(self, h, inter):
+        super().__init__()
+        self.gate_proj, self.up_proj = nn.Linear(h, inter, bias=False), nn.Linear(h, inter, bias=False)
+        self.down_proj = nn.Linear(inter, h, bias=False)
+        self.act_fn = nn.SiLU()
+
+    def forward(self, x):
+        return self.down_proj(self.act_fn(self.gate_proj(x)) * self.up_proj(x))
+
+
+def test_fuse_gated_mlps_on_an_hf_style_block(cuda):
+    """fuse_gated_mlps(model): the block's forward runs as two launches for decode-sized inputs (counted by the
+    library) and agrees with the unfused converted block; prefill-sized inputs still work."""
+    from torch_bnb_fp4_b200._lib import lib
+    torch.manual_seed(11)
+    mlp = _HFMLP(1024, 2816).to(cuda).half()
+    import copy
+    plain = torch_bnb_fp4.recursively_replace_with_fp4_linear(copy.deepcopy(mlp), as_dtype=torch.float16)
+    fused = torch_bnb_fp4.recursively_replace_with_fp4_linear(copy.deepcopy(mlp), as_dtype=torch.float16)
+    assert torch_bnb_fp4.fuse_gated_mlps(fused) == 1
+    for rows in (1, 3, 64):
+        x = torch.randn(rows, 1024, device=cuda, dtype=torch.float16)
+        fused(x)
+        n0 = lib.fp4_b200_launch_count()
+        y = fused(x)
+        n1 = lib.fp4_b200_launch_count()
+        if rows <= 8:
+            assert n1 - n0 == 2, n1 - n0
+        assert normwise(y.float().cpu().numpy(), plain(x).float().cpu().numpy()) <= 4e-3
+    res = torch.randn(2, 1024, device=cuda, dtype=torch.float16)
+    x = torch.randn(2, 1024, device=cuda, dtype=torch.float16)
+    y = fused.__dict__["_fp4_fused_mlp"](x, residual=res)
+    assert normwise(y.float().cpu().numpy(), (plain(x).float() + res.float()).cpu().numpy()) <= 4e-3

@@ -441,6 +441,92 @@ class TorchFP4LinearGroup(nn.Module):
         return tuple(m(x) for m in self.layers)
 
 
+def _unwrap(m):
+    return m.layer if isinstance(m, _GroupMember) else m
+
+
+def _decode_ready(qds, x) -> bool:
+    """the fused epilogues cover what the streaming GEMV covers: bitsandbytes table, blocksize 64, fp32 absmax,
+    1..8 rows of a contiguous CUDA input"""
+    k = x.shape[-1]
+    rows = x.numel() // k if k else 0
+    return (0 < rows <= GEMV_MAX_BATCH and x.is_cuda and all(
+        q.nested is None and q.absmax is not None and q._code_is_std and q.blocksize == 64 and q.N == k for q in qds))
+
+
+def linear_add(layer, x: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    """``layer(x) + residual`` with the addition in the GEMV epilogue for decode-sized inputs (the residual stream
+    around an o / down projection: one launch instead of two, the sum rounded once)."""
+    layer = _unwrap(layer)
+    qd = layer.quant_data
+    if _decode_ready([qd], x) and residual.dtype == x.dtype:
+        if x.dtype != qd.o_type:
+            qd.set_compute_type(x)
+        xc = x if x.is_contiguous() else x.contiguous()
+        outs = _ext.gemv_fp4_fused(xc, [qd.A], [qd.absmax], 64, qd.qtype, [qd._Bshape], [qd._bias_t],
+                                   residuals=[residual.contiguous()])
+        if outs is not None:
+            return outs[0]
+    return layer(x) + residual
+
+
+class TorchFP4GatedMLP(nn.Module):
+    """Extension: ``down(act(gate(x)) * up(x)) [+ residual]`` of a Llama / Mistral MLP block.
+    For decode-sized inputs the gate and up projections run as ONE launch whose epilogue applies the activation
+    and the product (the intermediate [rows, inter] tensors of the unfused form are never written), and the
+    residual is added in the down projection's epilogue: two launches instead of three GEMVs plus two or three
+    elementwise kernels.  Anything else (prefill) composes the layers' own paths."""
+
+    def __init__(self, gate, up, down, act: str = "silu"):
+        super().__init__()
+        if act not in ("silu", "gelu_tanh"):
+            raise ValueError("act must be 'silu' or 'gelu_tanh'")
+        self.gate_proj, self.up_proj, self.down_proj, self.act = _unwrap(gate), _unwrap(up), _unwrap(down), act
+
+    def _act(self, v):
+        return torch.nn.functional.silu(v) if self.act == "silu" else torch.nn.functional.gelu(v, approximate="tanh")
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        g, u = self.gate_proj.quant_data, self.up_proj.quant_data
+        if _decode_ready([g, u], x) and g.M == u.M:
+            for q in (g, u):
+                if x.dtype != q.o_type:
+                    q.set_compute_type(x)
+            xc = x if x.is_contiguous() else x.contiguous()
+            outs = _ext.gemv_fp4_fused(xc, [g.A, u.A], [g.absmax, u.absmax], 64, g.qtype, [g._Bshape, u._Bshape],
+                                       [g._bias_t, u._bias_t], gate_act=self.act)
+            if outs is not None:
+                h = outs[0]
+                return self.down_proj(h) if residual is None else linear_add(self.down_proj, h, residual)
+        h = self._act(self.gate_proj(x)) * self.up_proj(x)
+        y = self.down_proj(h)
+        return y if residual is None else y + residual
+
+
+def fuse_gated_mlps(model: nn.Module) -> int:
+    """Opt-in: give every sub-module that looks like an HF gated MLP - TorchFP4Linear children named gate_proj /
+    up_proj / down_proj and an ``act_fn`` that is SiLU or tanh-GELU, forward = down(act(gate(x)) * up(x)) - a forward
+    that runs through TorchFP4GatedMLP.  Returns the number of blocks fused."""
+    import types
+    made = 0
+    for mod in model.modules():
+        subs = [getattr(mod, n, None) for n in ("gate_proj", "up_proj", "down_proj")]
+        if not all(isinstance(_unwrap(m), TorchFP4Linear) for m in subs if m is not None) or None in subs:
+            continue
+        act_fn = getattr(mod, "act_fn", None)
+        if isinstance(act_fn, nn.SiLU):
+            act = "silu"
+        elif isinstance(act_fn, nn.GELU) and getattr(act_fn, "approximate", "none") == "tanh":
+            act = "gelu_tanh"
+        else:
+            continue
+        fused = TorchFP4GatedMLP(*subs, act=act)
+        mod.__dict__["_fp4_fused_mlp"] = fused  # not registered: the block keeps owning its layers
+        mod.forward = types.MethodType(lambda self, x: self.__dict__["_fp4_fused_mlp"](x), mod)
+        made += 1
+    return made
+
+
 class _GroupMember(nn.Module):
     """One projection of a TorchFP4LinearGroup that is called like a plain nn.Linear: the FIRST member called with
     a new input runs the whole group in one launch and parks the siblings' outputs; the siblings return them when

@@ -22,6 +22,7 @@ EXPORTS = [
     "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
     "fp4_b200_quantize", "fp4_b200_layer_create", "fp4_b200_layer_gemv", "fp4_b200_layer_destroy",
     "fp4_b200_layer_create_grouped", "fp4_b200_layer_gemv_grouped", "fp4_b200_launch_count",
+    "fp4_b200_gemv_grouped_ex",
 ]
 
 
@@ -37,6 +38,14 @@ class TpExchange(ctypes.Structure):
     _fields_ = [("in_world", ctypes.c_int), ("in_base", ctypes.c_void_p), ("slot_bytes", ctypes.c_uint32),
                 ("out_world", ctypes.c_int), ("out_rank", ctypes.c_int), ("out_peer_base", ctypes.c_void_p * 8),
                 ("epochs", ctypes.c_void_p), ("err", ctypes.c_void_p)]
+
+
+class Epilogue(ctypes.Structure):
+    """fp4_b200_epilogue_t"""
+    _fields_ = [("gate_act", ctypes.c_int), ("residual", ctypes.POINTER(ctypes.c_void_p))]
+
+
+GATE_ACT = {"silu": 1, "gelu_tanh": 2}
 
 
 def _load() -> ctypes.CDLL:
@@ -66,6 +75,9 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_gemv_grouped_tp.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                              ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32,
                                              ctypes.POINTER(TpExchange), vp]
+    lib.fp4_b200_gemv_grouped_ex.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                             ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32,
+                                             ctypes.POINTER(TpExchange), ctypes.POINTER(Epilogue), vp]
     lib.fp4_b200_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp,
                                   ctypes.c_size_t, vp]
     lib.fp4_b200_quantize.argtypes = [vp, i32, i64, i32, vp, vp, vp]

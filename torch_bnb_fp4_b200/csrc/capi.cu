@@ -34,7 +34,7 @@ bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int b
                                  const uint8_t* const* packed, const float* const* absmax);
 int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                                const void* const* bias, void* const* out, const int* N, int batch, int K, int dtype,
-                               const fp4_b200_tp_t* tp, cudaStream_t st);
+                               const fp4_b200_tp_t* tp, const fp4_b200_epilogue_t* epi, cudaStream_t st);
 int gemm_tcgen05_dispatch(const void*, const uint8_t*, const float*, const float*, const void*,
                           void*, int, int, int, int, int, unsigned, cudaStream_t);
 }  // namespace fp4b200
@@ -160,17 +160,20 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                                  bs_log2, dtype, (cudaStream_t)stream));
 }
 
-int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+int fp4_b200_gemv_grouped_ex(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                              const void* const* bias, void* const* out, const int* N, int batch, int K,
-                             int blocksize, int dtype, unsigned flags, const fp4_b200_tp_t* tp, void* stream) {
+                             int blocksize, int dtype, unsigned flags, const fp4_b200_tp_t* tp,
+                             const fp4_b200_epilogue_t* epi, void* stream) {
     const bool peer_x = tp && tp->in_world > 1;
     if ((!x && !peer_x) || !packed || !absmax || !out || !N) return FP4_B200_ERR_NULL;
     if (nmat < 1 || nmat > 4) return FP4_B200_ERR_SHAPE;
     if (batch < 1 || batch > 8) return FP4_B200_ERR_BATCH;
     if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16 && dtype != FP4_B200_F32) return FP4_B200_ERR_DTYPE;
     if (!(flags & FP4_B200_FLAG_CODE_IS_BNB_FP4)) return FP4_B200_ERR_UNSUPPORTED;  // bitsandbytes table only
+    const bool gated = epi && epi->gate_act;
     for (int m = 0; m < nmat; ++m)
-        if (!packed[m] || !absmax[m] || (!out[m] && !(tp && tp->out_world > 1))) return FP4_B200_ERR_NULL;
+        if (!packed[m] || !absmax[m] || (!out[m] && !(tp && tp->out_world > 1) && !(gated && m == 1)))
+            return FP4_B200_ERR_NULL;
     if (x && reinterpret_cast<uintptr_t>(x) % 16) return FP4_B200_ERR_ALIGN;
     if (tp) {
         if (tp->in_world < 0 || tp->in_world > 8 || tp->out_world < 0 || tp->out_world > 8) return FP4_B200_ERR_SHAPE;
@@ -184,8 +187,15 @@ int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* pack
     }
     if (!gemv_stream_group_supported(nmat, batch, N, K, blocksize, dtype, packed, absmax))
         return FP4_B200_ERR_UNSUPPORTED;
-    return counted(gemv_stream_group_dispatch(x, nmat, packed, absmax, bias, out, N, batch, K, dtype, tp,
+    return counted(gemv_stream_group_dispatch(x, nmat, packed, absmax, bias, out, N, batch, K, dtype, tp, epi,
                                       (cudaStream_t)stream));
+}
+
+int fp4_b200_gemv_grouped_tp(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
+                             const void* const* bias, void* const* out, const int* N, int batch, int K,
+                             int blocksize, int dtype, unsigned flags, const fp4_b200_tp_t* tp, void* stream) {
+    return fp4_b200_gemv_grouped_ex(x, nmat, packed, absmax, bias, out, N, batch, K, blocksize, dtype, flags, tp,
+                                    nullptr, stream);
 }
 
 int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,

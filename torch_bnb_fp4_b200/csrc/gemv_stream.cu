@@ -97,6 +97,14 @@ struct Params {
     float voffset[kMaxGroup];
     int vbs2_log2[kMaxGroup];
     uint32_t nested_mask;
+    // fused neighbours of the Linear:
+    //  gated != 0: matrices 0 / 1 are the gate / up projection of an MLP (same N, same K).  A row tile is then 8 rows
+    //    of EACH (MMA rows g = gate row, g + 8 = up row of the same index), so one lane ends up holding both values
+    //    of an output element and writes act(gate) * up - one output [batch, N], no intermediate tensors
+    //    (gated: 1 = SiLU, 2 = GELU tanh approximation);
+    //  vres[m] != NULL: a residual [batch, N_m] of dtype T added to the output (o / down projections).
+    int gated;
+    const void* vres[kMaxGroup];
     uint32_t tstart[kMaxGroup];    // first global tile of matrix m (tstart[0] = 0; unused entries = UINT32_MAX)
     int batch, K;
     uint32_t upt;     // units per row tile = ceil(K / 512)
@@ -166,6 +174,15 @@ __device__ __forceinline__ void cp_async_wait_pending(uint32_t pending) {  // un
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
         default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
     }
+}
+
+// activation of the gate in a gated MLP epilogue: 1 = SiLU (x * sigmoid(x)), 2 = GELU, tanh approximation
+__device__ __forceinline__ float gate_act(float v, int kind) {
+    if (kind == 2) {
+        const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+        return 0.5f * v * (1.f + tanhf(u));
+    }
+    return v / (1.f + __expf(-v));
 }
 
 // ---- tensor-parallel exchange through peer (symmetric) memory -------------------------------------------
@@ -272,7 +289,11 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         return (int)(gt >= p.tstart[1]) + (int)(gt >= p.tstart[2]) + (int)(gt >= p.tstart[3]);
     };
     // loader: lane (g, t) reads 16 B of row g and 16 B of row g + 8 per 128-k step; 4 steps per unit
-    const uint32_t row8 = 8 * rowb;
+    // byte distance from a lane's first weight row (MMA row g) to its second (MMA row g + 8): eight rows further
+    // down the same matrix, or the same row of the up projection in gated mode
+    const bool gated = p.gated != 0;
+    const size_t row8 = gated ? (size_t)(p.vpacked[1] - p.vpacked[0]) : (size_t)8 * rowb;
+    const uint32_t trows = gated ? 8u : 16u;  // weight rows of one matrix per row tile
     const uint8_t* wp;
     const float* ap;  // absmax of a unit: 16 rows x 8 blocks; lane (g, t) holds row g + 8 (t & 1), blocks 4 (t >> 1) ..
     const uint8_t* qp = nullptr;  // nested: this lane's four uint8 codes ...
@@ -281,9 +302,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     uint32_t ld_gt = tile0 + tl_a;
     auto loader_at = [&](uint32_t gt, uint32_t kunit) {
         const int m = mat_of(gt);
-        const size_t trow = (size_t)gt * 16;
+        const size_t trow = (size_t)gt * trows;
         wp = p.vpacked[m] + (trow + g) * rowb + kunit * 256 + t * 16;
-        ap = p.vabsmax[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
+        if (gated) ap = p.vabsmax[t & 1] + (trow + g) * nkb + kunit * 8 + 4 * (t >> 1);
+        else ap = p.vabsmax[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
         ld_nested = (p.nested_mask >> m) & 1u;
         if (ld_nested) {
             qp = p.vqabs[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
@@ -516,10 +538,11 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 
     // finish this warp's share (cnt units) of CTA-local tile tl
     auto flush = [&](uint32_t tl, uint32_t cnt) {
-        const uint32_t row0 = (tile0 + tl) * 16;
+        const uint32_t row0 = (tile0 + tl) * trows;
         const bool whole = cnt == p.upt;
         const int mm = mat_of(tile0 + tl);
         const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
+        const T* res = reinterpret_cast<const T*>(p.vres[mm]);
         T* out = reinterpret_cast<T*>(p.vout[mm]);
         const size_t Nm = (size_t)p.Nm[mm];
         float* part = myPart + (tl == tl_a ? 0 : batch * 16);
@@ -566,11 +589,20 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             }
             }
             if (owner && b < batch) {
-                if (whole) {
+                if (whole && gated) {  // v0 = gate row, v1 = up row of output element row0 + g
+                    const uint32_t r0 = row0 + g;
+                    if (bias) v0 += DT<T>::to_f32(bias[r0]);
+                    if (p.vbias[1]) v1 += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[1])[r0]);
+                    out[(size_t)b * Nm + r0] = DT<T>::from_f32(gate_act(v0, p.gated) * v1);
+                } else if (whole) {
                     const uint32_t r0 = row0 + g, r1 = r0 + 8;
                     if (bias) {
                         v0 += DT<T>::to_f32(bias[r0]);
                         v1 += DT<T>::to_f32(bias[r1]);
+                    }
+                    if (res) {
+                        v0 += DT<T>::to_f32(res[(size_t)b * Nm + r0]);
+                        v1 += DT<T>::to_f32(res[(size_t)b * Nm + r1]);
                     }
                     if (out_world > 1) {
                         if constexpr (sizeof(T) == 2) {
@@ -770,10 +802,26 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 const uint32_t w_tl = p.by_upt.div(w_ua);
                 v += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e];
             }
-            const uint32_t row = (tile0 + tt) * 16 + (e & 15), b = e >> 4;
+            const uint32_t b = e >> 4;
+            if (gated) {  // e & 15 < 8: the gate partial sums; the up row's are 8 entries further
+                if (e & 8u) continue;
+                float u = 0.f;
+                for (uint32_t w = wa; w <= wz; ++w) {
+                    const uint32_t w_ua = w * wq + (w < wr ? w : wr);
+                    const uint32_t w_tl = p.by_upt.div(w_ua);
+                    u += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e + 8];
+                }
+                const uint32_t row = (tile0 + tt) * 8 + (e & 7);
+                if (p.vbias[0]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[0])[row]);
+                if (p.vbias[1]) u += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[1])[row]);
+                reinterpret_cast<T*>(p.vout[0])[(size_t)b * p.Nm[0] + row] = DT<T>::from_f32(gate_act(v, p.gated) * u);
+                continue;
+            }
+            const uint32_t row = (tile0 + tt) * 16 + (e & 15);
             const int mm = mat_of(tile0 + tt);
             const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
+            if (p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
             if (out_world > 1) {
                 if constexpr (sizeof(T) == 2) {
                     const uint32_t w_ = tp_word<T>(v, out_tag);
@@ -823,8 +871,10 @@ struct Group {
     const float* absmax[kMaxGroup];
     const fp4_b200_nested_t* nested[kMaxGroup];  // non-NULL: absmax[m] is ignored
     const void* bias[kMaxGroup];
+    const void* residual[kMaxGroup];
     void* out[kMaxGroup];
     int N[kMaxGroup];
+    int gated;  // 0, or the gate activation: matrices 0 / 1 = gate / up, out[0] = act(gate) * up
 };
 
 // how a launch deals the row tiles to CTAs and sizes the per-warp rings
@@ -875,7 +925,20 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
     for (int m = 0; m < kMaxGroup; ++m) {
         p.vqabs[m] = nullptr; p.vcode2[m] = nullptr; p.vabs2[m] = nullptr; p.voffset[m] = 0.f; p.vbs2_log2[m] = 0;
     }
+    p.gated = gr.gated;
+    for (int m = 0; m < kMaxGroup; ++m) p.vres[m] = nullptr;
     uint32_t tiles = 0;
+    if (gr.gated) {  // one logical matrix of N / 8 tiles; nothing is rebased
+        for (int m = 0; m < kMaxGroup; ++m) {
+            p.tstart[m] = m == 0 ? 0u : 0xffffffffu;
+            p.vpacked[m] = m < 2 ? gr.packed[m] : nullptr;
+            p.vabsmax[m] = m < 2 ? gr.absmax[m] : nullptr;
+            p.vbias[m] = m < 2 ? gr.bias[m] : nullptr;
+            p.vout[m] = m == 0 ? gr.out[0] : nullptr;
+            p.Nm[m] = m < 2 ? gr.N[0] : 0;
+        }
+        tiles = (uint32_t)gr.N[0] / 8;
+    } else
     for (int m = 0; m < kMaxGroup; ++m) {
         if (m < gr.nmat) {
             // rebase to global rows (integer arithmetic on addresses; never dereferenced outside the matrix)
@@ -893,6 +956,7 @@ static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t
             }
             p.vbias[m] = gr.bias[m] ? reinterpret_cast<const uint8_t*>(gr.bias[m]) - grow0 * sizeof(T) : nullptr;
             p.vout[m] = reinterpret_cast<uint8_t*>(gr.out[m]) - grow0 * sizeof(T);
+            p.vres[m] = gr.residual[m] ? reinterpret_cast<const uint8_t*>(gr.residual[m]) - grow0 * sizeof(T) : nullptr;
             p.Nm[m] = gr.N[m];
             tiles += (uint32_t)gr.N[m] / 16;
         } else {
@@ -1009,13 +1073,20 @@ bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int b
 
 int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                                const void* const* bias, void* const* out, const int* N, int batch, int K, int dtype,
-                               const fp4_b200_tp_t* tp, cudaStream_t st) {
+                               const fp4_b200_tp_t* tp, const fp4_b200_epilogue_t* epi, cudaStream_t st) {
     Group gr = {};
     gr.tp = tp;
     gr.nmat = nmat;
     for (int m = 0; m < nmat; ++m) {
         gr.packed[m] = packed[m]; gr.absmax[m] = absmax[m]; gr.bias[m] = bias ? bias[m] : nullptr;
         gr.out[m] = out[m]; gr.N[m] = N[m];
+        gr.residual[m] = (epi && epi->residual) ? epi->residual[m] : nullptr;
+    }
+    if (epi && epi->gate_act) {
+        const bool tp_on = tp && (tp->in_world > 1 || tp->out_world > 1);
+        if (nmat != 2 || N[0] != N[1] || N[0] % 8 || epi->gate_act < 1 || epi->gate_act > 2 || tp_on || epi->residual)
+            return FP4_B200_ERR_UNSUPPORTED;
+        gr.gated = epi->gate_act;
     }
     return dispatch_group(x, gr, batch, K, dtype, st);
 }

@@ -383,6 +383,65 @@ def gemv_fp4_grouped(A: Optional[torch.Tensor], Bs: Sequence[torch.Tensor], absm
     return list(outs)
 
 
+def gemv_fp4_fused(A: torch.Tensor, Bs: Sequence[torch.Tensor], absmaxes: Sequence[torch.Tensor], blocksize: int, dtype,
+                   Bshapes: Sequence[Sequence[int]], biases: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                   gate_act: Optional[str] = None, residuals: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    """Extension: the grouped fused dequant-GEMV with the neighbouring elementwise ops in its
+    epilogue.  gate_act = "silu" / "gelu_tanh": Bs = (gate, up) of a gated MLP, returns ONE tensor
+    act(x W_gate^T + b_gate) * (x W_up^T + b_up) computed in fp32 before the single rounding to the output dtype.
+    residuals: tensors [..., N_m] added to the outputs (the residual stream around o / down).  Returns a list of
+    outputs, or None when the shapes are outside the streaming kernel (the caller composes the ops itself)."""
+    dt = get_scalar_type(dtype)
+    n = len(Bs)
+    k = int(Bshapes[0][1])
+    _check_in(A, "A")
+    if A.dtype != dt or A.shape[-1] != k or any(int(sh[1]) != k for sh in Bshapes):
+        raise RuntimeError("fused GEMV: A / weights disagree on dtype or in_features")
+    batch = A.numel() // k if k else 0
+    if n < 1 or n > 4 or batch < 1 or batch > 8:
+        return None
+    for B, am in zip(Bs, absmaxes):
+        _check_in(B, "B", torch.uint8)
+        _check_in(am, "absmax", torch.float32)
+    lead = tuple(A.shape[:-1])
+    vp = ctypes.c_void_p
+    epi = _lib.Epilogue()
+    n_out = 1 if gate_act else n
+    if gate_act:
+        if gate_act not in _lib.GATE_ACT or n != 2 or int(Bshapes[0][0]) != int(Bshapes[1][0]):
+            raise RuntimeError("gate_act needs the gate and up projections of one MLP (same out_features)")
+        epi.gate_act = _lib.GATE_ACT[gate_act]
+    outs = [torch.empty(lead + (int(Bshapes[i][0]),), dtype=dt, device=A.device) for i in range(n_out)]
+    keep = None
+    if residuals is not None and any(r is not None for r in residuals):
+        if gate_act:
+            raise RuntimeError("a residual goes with a plain projection, not with the gated pair")
+        for r, o in zip(residuals, outs):
+            if r is not None:
+                _check_in(r, "residual", dt)
+                if r.shape != o.shape:
+                    raise RuntimeError("residual must have the shape of the output")
+        keep = (vp * n)(*[None if r is None else r.data_ptr() for r in residuals])
+        epi.residual = ctypes.cast(keep, ctypes.POINTER(vp))
+    pk = (vp * n)(*[B.data_ptr() for B in Bs])
+    am = (vp * n)(*[a.data_ptr() for a in absmaxes])
+    ou = (vp * n)(*([o.data_ptr() for o in outs] + [None] * (n - n_out)))
+    ns = (ctypes.c_int * n)(*[int(sh[0]) for sh in Bshapes])
+    bi = None
+    if biases is not None and any(b is not None for b in biases):
+        for b in biases:
+            if b is not None:
+                _check_in(b, "bias", dt)
+        bi = (vp * n)(*[None if b is None else b.data_ptr() for b in biases])
+    with _on_device(A) as st:
+        status = lib.fp4_b200_gemv_grouped_ex(A.data_ptr(), n, pk, am, bi, ou, ns, batch, k, blocksize, _CODE_OF[dt],
+                                              _lib.FLAG_CODE_IS_BNB_FP4, None, ctypes.byref(epi), st)
+    if status == -7:
+        return None
+    check(status, "gemv_fp4_fused")
+    return outs
+
+
 class GroupLauncher:
     """Pre-validated launcher for a group of layers that share the input (see GemvLauncher): the pointer
     arrays of fp4_b200_gemv_grouped are built once, a call allocates the outputs and fills in their pointers."""
