@@ -65,11 +65,10 @@ enum {
     FP4_B200_FLAG_CODE_IS_BNB_FP4 = 1,
     /* force the generic CUDA-core GEMV (testing / A-B timing) */
     FP4_B200_FLAG_FORCE_GENERIC = 2,
-    /* do not use the TMA-staged GEMV; take the register-streamed tensor-core GEMV (testing / A-B timing) */
+    /* accepted and ignored (they selected GEMV kernel families of ABI version 1 that no longer exist) */
     FP4_B200_FLAG_NO_TMA = 4,
-    /* do not use the integer tensor-core GEMV (IMMA u8 x s8); take the fp16 tensor-core kernels (testing / A-B timing) */
     FP4_B200_FLAG_NO_I8 = 8,
-    /* do not use the default L2-prefetched streaming GEMV; take the stream-K kernels (testing / A-B timing) */
+    /* do not use the streaming integer tensor-core GEMV; take the generic CUDA-core kernel (testing / A-B timing) */
     FP4_B200_FLAG_NO_STREAM = 16
 };
 
@@ -140,11 +139,12 @@ int fp4_b200_absmax_denest(const fp4_b200_nested_t* nested, float* absmax_out, i
  * is NOT required (blocks may straddle rows as in bitsandbytes).
  * nested may be NULL (absmax is fp32) or non-NULL (absmax ignored, decoded in the kernel).
  *
- * workspace: device scratch of at least fp4_b200_gemv_workspace_bytes(N) bytes, 256-byte aligned,
- * ZERO-FILLED once by the caller before its first use (the kernel keeps its counters zero between
- * launches) and not shared by launches that may run concurrently (one per stream).  It holds the
- * partial sums of row tiles that the stream-K schedule splits between warps.  Passing NULL selects
- * the generic CUDA-core kernel, which needs none. */
+ * Requires for the streaming tensor-core kernel: bitsandbytes codebook (code == NULL or
+ * FP4_B200_FLAG_CODE_IS_BNB_FP4), blocksize 64, K % 256 == 0, N % 16 == 0, 16-byte aligned buffers; a batch whose
+ * activations do not fit shared memory together runs as two launches.  Anything else takes the generic kernel.
+ *
+ * workspace / workspace_bytes: ignored (no kernel needs scratch memory any more; fp4_b200_gemv_workspace_bytes
+ * returns 0).  The parameters remain so that callers of ABI version 1 keep working. */
 int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                   const fp4_b200_nested_t* nested, const float* code, const void* bias, void* out,
                   int batch, int N, int K, int blocksize, int dtype, unsigned flags,
@@ -179,7 +179,7 @@ int fp4_b200_layer_gemv_grouped(const fp4_b200_layer_t* layer, const void* x, vo
  * of a decoder layer, which the reference issues as separate gemv_fp4 calls
  * (torch_bnb_fp4/__init__.py:471-492 once per nn.Linear).  The arrays are HOST arrays of device pointers /
  * sizes.  bias may be NULL, or hold NULL entries.  Results equal nmat fp4_b200_gemv calls up to fp32 summation order (deterministic).
- * Requires FP4_B200_FLAG_CODE_IS_BNB_FP4, blocksize 64, K % 512 == 0, every N[m] % 16 == 0; otherwise
+ * Requires FP4_B200_FLAG_CODE_IS_BNB_FP4, blocksize 64, K % 256 == 0, every N[m] % 16 == 0; otherwise
  * FP4_B200_ERR_UNSUPPORTED (the caller then issues the calls one by one). */
 int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                           const void* const* bias, void* const* out, const int* N, int batch, int K,

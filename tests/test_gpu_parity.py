@@ -129,8 +129,7 @@ def _gemv_case(cuda, dtype, N, K, batch, bs=64, seed=0, bias=False, flags=0, cod
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N,K", [(256, 256), (64, 2048), (2048, 768), (1024, 4096), (48, 14336), (4096, 4096)])
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_STREAM, _lib.FLAG_NO_STREAM | _lib.FLAG_NO_I8,
-                                   _lib.FLAG_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_STREAM, _lib.FLAG_FORCE_GENERIC])
 def test_gemv_batch1_vs_fp64_oracle(cuda, dtype, N, K, flags):
     y, exact, _ = _gemv_case(cuda, dtype, N, K, 1, seed=N + K, flags=flags)
     assert y.shape == (1, N) and y.dtype == dtype
@@ -139,7 +138,7 @@ def test_gemv_batch1_vs_fp64_oracle(cuda, dtype, N, K, flags):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("batch", [2, 3, 4, 5, 7, 8])
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_I8, _lib.FLAG_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC])
 def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
     y, exact, _ = _gemv_case(cuda, dtype, 512, 1024, batch, seed=batch, bias=True, flags=flags)
     assert y.shape == (batch, 512)
@@ -154,7 +153,9 @@ def test_gemv_batched_with_bias(cuda, dtype, batch, flags):
                                        (1024, 1792, 1), (2048, 256, 2), (1536, 768, 3),
                                        # block-aligned variant (more than 8 (row, term) columns): 16-bit batch
                                        # 5..8, fp32 batch 3..8; half units, ragged tiles
-                                       (2400, 1024, 6), (1024, 768, 7), (2368, 1280, 8), (1536, 256, 5)])
+                                       (2400, 1024, 6), (1024, 768, 7), (2368, 1280, 8), (1536, 256, 5),
+                                       # few row tiles (k/v projections, tensor-parallel shards): 1, 4, 8, 32 tiles
+                                       (16, 4096, 1), (64, 2048, 8), (128, 8192, 1), (512, 14336, 2), (128, 1792, 4)])
 def test_gemv_stream_kernel_shapes(cuda, dtype, N, K, batch):
     y, exact, _ = _gemv_case(cuda, dtype, N, K, batch, seed=N + K + batch, bias=(batch % 2 == 0))
     assert y.shape == (batch, N)

@@ -12,8 +12,9 @@ from tools.microbench import graph_time  # noqa: E402
 
 dev = torch.device("cuda:0")
 code = torch.tensor(ext.BNB_FP4_CODE, device=dev)
-FAM = {"default": 0, "no_stream": _lib.FLAG_NO_STREAM, "no_stream_no_i8": _lib.FLAG_NO_STREAM | _lib.FLAG_NO_I8,
-       "imma_only": _lib.FLAG_NO_STREAM | _lib.FLAG_NO_I8 | _lib.FLAG_NO_TMA, "generic": _lib.FLAG_FORCE_GENERIC}
+# (round 2: the stream-K families gemv_i8 / gemv_tma / gemv_imma lost on every shape below - see
+# profiles/r02_gemv_family_sweep.log - and were removed; what is left to compare is the generic kernel)
+FAM = {"stream": 0, "generic": _lib.FLAG_FORCE_GENERIC}
 for shp in sys.argv[1:] or ["128x4096", "256x4096", "512x4096", "768x4096", "1024x4096", "512x14336", "2048x768", "64x2048",
                             "1024x8192", "128x8192", "3584x8192"]:
     N, K = map(int, shp.split("x"))

@@ -63,7 +63,6 @@ def main():
     ap.add_argument("--batch", type=int, nargs="+", default=[1])
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--no-dequant", action="store_true")
-    ap.add_argument("--no-i8", action="store_true")
     ap.add_argument("--shapes", nargs="*", default=["4096x4096", "1024x4096", "14336x4096", "4096x14336",
                                                      "8192x8192", "28672x8192"])
     a = ap.parse_args()
@@ -71,7 +70,7 @@ def main():
     st = {"bf16": ext.bfloat16, "fp16": ext.float16, "fp32": ext.float32}[a.dtype]
     dev = torch.device("cuda:0")
     code = torch.tensor(ext.BNB_FP4_CODE, device=dev)
-    flags = _lib.FLAG_FORCE_GENERIC if a.generic else (_lib.FLAG_NO_I8 if a.no_i8 else 0)
+    flags = _lib.FLAG_FORCE_GENERIC if a.generic else 0
     for shp in a.shapes:
         N, K = map(int, shp.split("x"))
         wbytes = N * K // 2

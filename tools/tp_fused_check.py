@@ -46,6 +46,22 @@ print(f"[rank {rank}] nccl vs full {((ref_nccl - ref_full).abs().max() / scale).
 allout = [torch.empty_like(outs[0]) for _ in range(world)]
 dist.all_gather(allout, outs[0])
 print(f"[rank {rank}] ranks agree bit for bit: {all(torch.equal(allout[0], o) for o in allout)}", flush=True)
+# varying batch sizes with the ranks deliberately out of step (the consumer waits for late peers; a peer that
+# never delivers traps after 20 s instead of being summed as garbage)
+import time  # noqa: E402
+worst = 0.0
+with torch.no_grad():
+    step_n = bench.make_step(tp_layers, world)
+    for it, b in enumerate((1, 3, 2, 8, 1, 5)):
+        xb = torch.randn(b, cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(40 + it)).bfloat16()
+        if it % 2 == rank % 2:
+            torch.cuda.synchronize()
+            time.sleep(0.05)
+        got = step_p(xb).float()
+        want = step_n(xb).float()
+        worst = max(worst, ((got - want).abs().max() / want.abs().max()).item())
+    ex.check()
+print(f"[rank {rank}] skewed ranks, batch 1..8: peer vs nccl worst {worst:.2e}", flush=True)
 g = GraphedCallable(step_p, [h0], warmup=3)
 for _ in range(5):
     og = g(h0).float()

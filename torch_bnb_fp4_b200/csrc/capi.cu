@@ -1,5 +1,5 @@
 // extern "C" surface of libfp4_b200.so (declared in include/fp4_b200.h): argument validation and
-// kernel selection only; the kernels live in dequant.cu, gemv_generic.cu, gemv_imma.cu, gemm_tcgen05.cu.
+// kernel selection only; the kernels live in dequant.cu, gemv_stream.cu, gemv_generic.cu, gemm_tcgen05.cu, quantize.cu.
 #include <atomic>
 #include <new>
 
@@ -13,19 +13,6 @@ int quantize_dispatch(const void*, int, int64_t, int, uint8_t*, float*, cudaStre
 int gemv_generic_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*,
                           const NestedDev&, const float*, const void*, void*, int, int, int, int,
                           int, cudaStream_t);
-int gemv_imma_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*,
-                       const NestedDev&, const void*, void*, void*, size_t, int, int, int, int, int,
-                       cudaStream_t);
-bool gemv_imma_supported(int batch, int N, int K, int blocksize, int dtype);
-size_t gemv_imma_workspace_bytes(int N);
-bool gemv_tma_supported(int batch, int N, int K, int blocksize, int dtype, bool nested,
-                        const void* packed, const void* absmax);
-int gemv_tma_dispatch(const void*, const uint8_t*, const float*, const void*, void*, void*, size_t,
-                      int, int, int, int, cudaStream_t);
-bool gemv_i8_supported(int batch, int N, int K, int blocksize, int dtype, bool nested,
-                       const void* packed, const void* absmax);
-int gemv_i8_dispatch(const void*, const uint8_t*, const float*, const void*, void*, void*, size_t, int,
-                     int, int, int, cudaStream_t);
 bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested,
                            const void* packed, const void* absmax);
 int gemv_stream_dispatch(const void*, const uint8_t*, const float*, const fp4_b200_nested_t*, const void*, void*, int,
@@ -115,26 +102,24 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
         if (l2 < 0) return FP4_B200_ERR_BLOCKSIZE;
         nd = NestedDev{nested->qabsmax, nested->code2, nested->absmax2, nested->offset, l2};
     }
+    (void)workspace;
+    (void)workspace_bytes;
     const bool std_code = (code == nullptr) || (flags & FP4_B200_FLAG_CODE_IS_BNB_FP4);
-    if (std_code && !(flags & FP4_B200_FLAG_FORCE_GENERIC) && workspace &&
-        gemv_imma_supported(batch, N, K, blocksize, dtype)) {
-        if (workspace_bytes < gemv_imma_workspace_bytes(N)) return FP4_B200_ERR_WORKSPACE;
-        // default: L2-prefetched register-streamed integer tensor-core kernel (whole row tiles per CTA)
-        if (!(flags & FP4_B200_FLAG_NO_STREAM) &&
-            gemv_stream_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed,
-                                  nested ? (const void*)nested->qabsmax : (const void*)absmax))
+    if (std_code && !(flags & (FP4_B200_FLAG_FORCE_GENERIC | FP4_B200_FLAG_NO_STREAM))) {
+        const void* aq = nested ? (const void*)nested->qabsmax : (const void*)absmax;
+        // the streaming integer tensor-core kernel (bitsandbytes table, blocksize 64, K % 256 == 0, N % 16 == 0)
+        if (gemv_stream_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, aq))
             return counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, batch, N, K, dtype,
-                                        (cudaStream_t)stream));
-        // the rows of x (as integer terms) that do not fit the streaming kernel's shared memory together - fp32
-        // inputs with batch 5..8 on K = 8192, 16-bit batch 8 on K = 14336 ... - are done in two launches: the
-        // weights stream twice, which is still an order of magnitude faster than the kernels below
-        if (batch >= 2 && !(flags & FP4_B200_FLAG_NO_STREAM)) {
+                                                (cudaStream_t)stream));
+        // rows of x (as integer terms) that do not fit its shared memory together - fp32 inputs with batch 5..8 on
+        // K = 8192, 16-bit batch 8 on K = 14336 ... - are done in two launches: the weights stream twice, which is
+        // still an order of magnitude faster than the generic kernel
+        if (batch >= 2) {
             const int b0 = (batch + 1) / 2, b1 = batch - b0;
-            const void* aq = nested ? (const void*)nested->qabsmax : (const void*)absmax;
             if (gemv_stream_supported(b0, N, K, blocksize, dtype, nested != nullptr, packed, aq)) {
                 const size_t es = dtype == FP4_B200_F32 ? 4 : 2;
-                int rc = counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, b0, N, K, dtype,
-                                                      (cudaStream_t)stream));
+                const int rc = counted(gemv_stream_dispatch(x, packed, absmax, nested, bias, out, b0, N, K, dtype,
+                                                            (cudaStream_t)stream));
                 if (rc) return rc;
                 return counted(gemv_stream_dispatch(static_cast<const uint8_t*>(x) + (size_t)b0 * K * es, packed,
                                                     absmax, nested, bias,
@@ -142,20 +127,8 @@ int fp4_b200_gemv(const void* x, const uint8_t* packed, const float* absmax,
                                                     dtype, (cudaStream_t)stream));
             }
         }
-        // stream-K integer tensor-core kernel (TMA-staged) where its layout requirements hold
-        if (!(flags & FP4_B200_FLAG_NO_I8) &&
-            gemv_i8_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
-            return counted(gemv_i8_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch, N,
-                                    K, dtype, (cudaStream_t)stream));
-        // fp16 tensor-core kernels: TMA-staged, else register-streamed (nested absmax, other block sizes)
-        if (!(flags & FP4_B200_FLAG_NO_TMA) &&
-            gemv_tma_supported(batch, N, K, blocksize, dtype, nested != nullptr, packed, absmax))
-            return counted(gemv_tma_dispatch(x, packed, absmax, bias, out, workspace, workspace_bytes, batch,
-                                     N, K, dtype, (cudaStream_t)stream));
-        return counted(gemv_imma_dispatch(x, packed, absmax, nested, nd, bias, out, workspace,
-                                  workspace_bytes, batch, N, K, bs_log2, dtype,
-                                  (cudaStream_t)stream));
     }
+    // any codebook, any block size (>= 32), K % 32 == 0: CUDA-core kernel
     return counted(gemv_generic_dispatch(x, packed, absmax, nested, nd, code, bias, out, batch, N, K,
                                  bs_log2, dtype, (cudaStream_t)stream));
 }
@@ -205,7 +178,10 @@ int fp4_b200_gemv_grouped(const void* x, int nmat, const uint8_t* const* packed,
                                     nullptr, stream);
 }
 
-size_t fp4_b200_gemv_workspace_bytes(int N) { return N > 0 ? gemv_imma_workspace_bytes(N) : 0; }
+size_t fp4_b200_gemv_workspace_bytes(int N) {
+    (void)N;
+    return 0;  // no kernel of this library needs scratch memory any more (kept for ABI compatibility)
+}
 
 struct fp4_b200_layer {
     int nmat;

@@ -251,8 +251,12 @@ __device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float
 }
 
 // HALF: K % 512 == 256, i.e. the last unit of every row tile holds two steps instead of four
-template <typename T, int NCT, bool HALF, bool ALIGNED>
+// EXTRA: the rarely used features - nested absmax, the gated-MLP / residual epilogues, the tensor-parallel exchange -
+// are compiled into a second instantiation, so the plain decode launch carries none of their code or registers
+template <typename T, int NCT, bool HALF, bool ALIGNED, bool EXTRA>
 __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(const __grid_constant__ Params p) {
+    const uint32_t nested_mask = EXTRA ? p.nested_mask : 0u;
+    const int gated_kind = EXTRA ? p.gated : 0;
     constexpr int TERMS = sizeof(T) == 4 ? 4 : 2;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     // loader: lane (g, t) reads 16 B of row g and 16 B of row g + 8 per 128-k step; 4 steps per unit
     // byte distance from a lane's first weight row (MMA row g) to its second (MMA row g + 8): eight rows further
     // down the same matrix, or the same row of the up projection in gated mode
-    const bool gated = p.gated != 0;
+    const bool gated = gated_kind != 0;
     const size_t row8 = gated ? (size_t)(p.vpacked[1] - p.vpacked[0]) : (size_t)8 * rowb;
     const uint32_t trows = gated ? 8u : 16u;  // weight rows of one matrix per row tile
     const uint8_t* wp;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         wp = p.vpacked[m] + (trow + g) * rowb + kunit * 256 + t * 16;
         if (gated) ap = p.vabsmax[t & 1] + (trow + g) * nkb + kunit * 8 + 4 * (t >> 1);
         else ap = p.vabsmax[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
-        ld_nested = (p.nested_mask >> m) & 1u;
+        ld_nested = (nested_mask >> m) & 1u;
         if (ld_nested) {
             qp = p.vqabs[m] + (trow + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
             const size_t lblk = ((size_t)(gt - p.tstart[m]) * 16 + g + 8 * (t & 1)) * nkb + kunit * 8 + 4 * (t >> 1);
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     TL_STAMP(2);
     // tensor parallel (see the helpers above).  Epochs: [0] = last published by this rank's producers,
     // [1] = last finished by its consumers; both only change between the kernels that read them.
-    const int in_world = p.tp.in_world, out_world = p.tp.out_world;
+    const int in_world = EXTRA ? p.tp.in_world : 0, out_world = EXTRA ? p.tp.out_world : 0;
     uint32_t in_tag = 0, out_tag = 0, e_in = 0, e_out = 0;
     const uint8_t* in_slot = nullptr;
     size_t out_off = 0;
@@ -380,10 +384,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
 
     // ---- 2. stage x as s8 residual terms, one power-of-two scale per (batch row, 64-block) ----------
     for (uint32_t i = tid; i < kZeroBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sZero)[i] = 0u;
-    if (p.nested_mask) {
+    if (nested_mask) {
         for (uint32_t i = tid; i < kMaxGroup * 256; i += kThreads) {
             const uint32_t m = i >> 8;
-            if ((p.nested_mask >> m) & 1u) sCode2[i] = __ldg(p.vcode2[m] + (i & 255u));
+            if ((nested_mask >> m) & 1u) sCode2[i] = __ldg(p.vcode2[m] + (i & 255u));
         }
     }
     {
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         const bool whole = cnt == p.upt;
         const int mm = mat_of(tile0 + tl);
         const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
-        const T* res = reinterpret_cast<const T*>(p.vres[mm]);
+        const T* res = EXTRA ? reinterpret_cast<const T*>(p.vres[mm]) : nullptr;
         T* out = reinterpret_cast<T*>(p.vout[mm]);
         const size_t Nm = (size_t)p.Nm[mm];
         float* part = myPart + (tl == tl_a ? 0 : batch * 16);
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                     const uint32_t r0 = row0 + g;
                     if (bias) v0 += DT<T>::to_f32(bias[r0]);
                     if (p.vbias[1]) v1 += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[1])[r0]);
-                    out[(size_t)b * Nm + r0] = DT<T>::from_f32(gate_act(v0, p.gated) * v1);
+                    out[(size_t)b * Nm + r0] = DT<T>::from_f32(gate_act(v0, gated_kind) * v1);
                 } else if (whole) {
                     const uint32_t r0 = row0 + g, r1 = r0 + 8;
                     if (bias) {
@@ -635,9 +639,9 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
         const uint32_t sl = ring_a + slot * kSlot;
         if constexpr (ALIGNED) __syncwarp();  // the lanes read each other's copies
         uint4 amc = lds_u4(ring_am + slot * kSlot);
-        if (p.nested_mask) {  // uniform
+        if (nested_mask) {  // uniform
             const int mm = mat_of(tile0 + tl);
-            if ((p.nested_mask >> mm) & 1u) {
+            if ((nested_mask >> mm) & 1u) {
                 // absmax = fp32_add(fp32_mul(code2[q], absmax2), offset): two separately rounded operations
                 const uint32_t codes = amc.x;
                 const float a2 = __uint_as_float(amc.y), off = p.voffset[mm];
@@ -814,14 +818,14 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 const uint32_t row = (tile0 + tt) * 8 + (e & 7);
                 if (p.vbias[0]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[0])[row]);
                 if (p.vbias[1]) u += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[1])[row]);
-                reinterpret_cast<T*>(p.vout[0])[(size_t)b * p.Nm[0] + row] = DT<T>::from_f32(gate_act(v, p.gated) * u);
+                reinterpret_cast<T*>(p.vout[0])[(size_t)b * p.Nm[0] + row] = DT<T>::from_f32(gate_act(v, gated_kind) * u);
                 continue;
             }
             const uint32_t row = (tile0 + tt) * 16 + (e & 15);
             const int mm = mat_of(tile0 + tt);
             const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
-            if (p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
+            if (EXTRA && p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
             if (out_world > 1) {
                 if constexpr (sizeof(T) == 2) {
                     const uint32_t w_ = tp_word<T>(v, out_tag);
@@ -903,9 +907,9 @@ static Partition partition(uint32_t tiles, int batch, int K, int nt) {
     return pt;
 }
 
-template <typename T, int NCT, bool HALF, bool ALIGNED>
+template <typename T, int NCT, bool HALF, bool ALIGNED, bool EXTRA>
 static int launch(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
-    auto kern = gemv_stream_kernel<T, NCT, HALF, ALIGNED>;
+    auto kern = gemv_stream_kernel<T, NCT, HALF, ALIGNED, EXTRA>;
     // the opt-in to large dynamic shared memory is per device (a process may drive several GPUs)
     static bool configured[64] = {};
     int dev = 0;
@@ -998,7 +1002,10 @@ template <typename T, int NT>
 static int launch_nct(const void* x, const Group& gr, int batch, int K, cudaStream_t st) {
     const int nct = column_tiles(batch, NT);
     const bool half = K % 512 != 0;
-#define FP4_GO(NCT, AL) (half ? launch<T, NCT, true, AL>(x, gr, batch, K, st) : launch<T, NCT, false, AL>(x, gr, batch, K, st))
+    bool extra = gr.gated != 0 || (gr.tp && (gr.tp->in_world > 1 || gr.tp->out_world > 1));
+    for (int m = 0; m < gr.nmat; ++m) extra = extra || gr.nested[m] || gr.residual[m];
+#define FP4_GO2(NCT, AL, HF) (extra ? launch<T, NCT, HF, AL, true>(x, gr, batch, K, st) : launch<T, NCT, HF, AL, false>(x, gr, batch, K, st))
+#define FP4_GO(NCT, AL) (half ? FP4_GO2(NCT, AL, true) : FP4_GO2(NCT, AL, false))
     if (use_aligned(batch, NT)) {
         if (nct <= 1) return FP4_GO(1, true);
         if (nct <= 2) return FP4_GO(2, true);
@@ -1007,6 +1014,7 @@ static int launch_nct(const void* x, const Group& gr, int batch, int K, cudaStre
     if (nct <= 1) return FP4_GO(1, false);
     if (nct <= 2) return FP4_GO(2, false);
     return FP4_GO(4, false);  // only with FP4_B200_GEMV_ALIGNED=0
+#undef FP4_GO2
 #undef FP4_GO
 }
 
@@ -1028,12 +1036,14 @@ extern "C" void fp4_b200_debug_stream_timeline(long long* buf) { g_stream_tl = b
 bool gemv_stream_supported(int batch, int N, int K, int blocksize, int dtype, bool nested, const void* packed,
                            const void* absmax) {
     static const int disabled = env_int("FP4_B200_GEMV_NO_STREAM", 0);
-    static const int min_tiles = env_int("FP4_B200_GEMV_STREAM_MIN_TILES", 48);
+    // (round 1 sent layers with fewer than 48 row tiles to stream-K kernels; measured again in round 2 this kernel is
+    // faster down to 4 tiles - profiles/r02_gemv_family_sweep.log - and those kernels are gone)
+    static const int min_tiles = env_int("FP4_B200_GEMV_STREAM_MIN_TILES", 1);
     (void)nested;  // decoded in the kernel
     if (disabled || blocksize != 64) return false;
     if (batch < 1 || batch > 8 || N <= 0 || K <= 0) return false;
     if (K % 256 != 0 || N % 16 != 0) return false;
-    if (N / 16 < min_tiles) return false;  // too few row tiles to occupy the GPU: the stream-K kernels split K
+    if (N / 16 < min_tiles) return false;
     if ((uint64_t)N * (uint64_t)K >= (1ull << 40)) return false;
     if (reinterpret_cast<uintptr_t>(packed) % 16 || reinterpret_cast<uintptr_t>(absmax) % 16) return false;
     const int nt = nterms(dtype);

@@ -118,23 +118,10 @@ def code_is_bnb_fp4(code: torch.Tensor) -> bool:
 
 
 # ---- GEMV workspace --------------------------------------------------------------------------------
-# The stream-K GEMV parks partial sums of row tiles shared between warps in a small scratch buffer
-# (include/fp4_b200.h).  One zero-filled buffer per (device, stream), grown on demand; launches on the
-# same stream are ordered, so sharing it between layers is safe.
-_workspaces: dict = {}
-
-
+# ABI version 1 kernels parked partial sums in a caller-provided scratch buffer; none of today's kernels needs one
+# (fp4_b200_gemv_workspace_bytes returns 0), so NULL is passed.
 def _gemv_workspace(device: torch.device, stream_ptr: int, n_out: int):
-    need = lib.fp4_b200_gemv_workspace_bytes(n_out)
-    key = (device.index, stream_ptr)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < need:
-        if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("GEMV workspace must be created before CUDA-graph capture: run the "
-                               "layer once eagerly (warm-up) on the capturing stream first")
-        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    return None
 
 
 def make_nested(qabsmax: torch.Tensor, code2: torch.Tensor, absmax2: torch.Tensor, offset: float,
@@ -235,13 +222,12 @@ def _gemv(A, B, absmax, datatype, blocksize, dtype, Bshape, bias, nested, flags,
     if datatype is not None and code_is_bnb_fp4(datatype):
         flags |= _lib.FLAG_CODE_IS_BNB_FP4
     with _on_device(A) as st:
-        ws = _gemv_workspace(A.device, st, n_out)
         check(lib.fp4_b200_gemv(
             A.data_ptr(), B.data_ptr(), None if absmax is None else absmax.data_ptr(),
             None if nested is None else ctypes.byref(nested),
             None if datatype is None else datatype.data_ptr(),
             None if bias is None else bias.data_ptr(), out.data_ptr(), batch, n_out, k, blocksize,
-            _CODE_OF[dt], flags, ws.data_ptr(), ws.numel(), st), what)
+            _CODE_OF[dt], flags, None, 0, st), what)
     return out
 
 
@@ -250,7 +236,7 @@ class GemvLauncher:
     done once here, the per-call work is one torch.empty, one raw-stream query and one ctypes call.  The
     launcher keeps the tensors alive, so the cached device pointers stay valid; anything it was not built
     for (another device current, non-contiguous input, another dtype) is the caller's slow path."""
-    __slots__ = ("keep", "handle", "n_out", "k", "dt", "dev", "idx", "ws_need", "what", "_shapes")
+    __slots__ = ("keep", "handle", "n_out", "k", "dt", "dev", "idx", "what", "_shapes")
 
     def __init__(self, B, absmax, datatype, blocksize, dtype, Bshape, bias):
         _check_in(B, "B", torch.uint8)
@@ -279,7 +265,6 @@ class GemvLauncher:
         if not self.handle:
             raise RuntimeError("fp4_b200_layer_create failed")
         self.dev, self.idx = B.device, B.device.index
-        self.ws_need = lib.fp4_b200_gemv_workspace_bytes(self.n_out)
         self.what = "gemv_fp4_bias"
         self._shapes = {}
 
@@ -298,10 +283,7 @@ class GemvLauncher:
             shp = self._shapes[A.shape] = tuple(A.shape[:-1]) + (self.n_out,)
         out = torch.empty(shp, dtype=self.dt, device=self.dev)
         st = torch._C._cuda_getCurrentRawStream(self.idx)
-        ws = _workspaces.get((self.idx, st))
-        if ws is None or ws.numel() < self.ws_need:
-            ws = _gemv_workspace(self.dev, st, self.n_out)
-        rc = lib.fp4_b200_layer_gemv(self.handle, A.data_ptr(), out.data_ptr(), batch, ws.data_ptr(), ws.numel(), st)
+        rc = lib.fp4_b200_layer_gemv(self.handle, A.data_ptr(), out.data_ptr(), batch, None, 0, st)
         if rc:
             check(rc, self.what)
         return out
