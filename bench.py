@@ -532,7 +532,10 @@ def run_ours(args, rank, world):
         # launch each), then called projection by projection like an unmodified HF decoder layer
         if nested:  # keep the absmax double-quantised: 0.516 instead of 0.5625 bytes per weight through the GEMV
             model = torch.nn.ModuleList([Block(m) for m in layers])
-            how = "TorchFP4Linear(materialize_nested_absmax=False) per projection: nested absmax decoded in the GEMV"
+            for blk in model:
+                torch_bnb_fp4.group_projections(blk)
+            how = ("TorchFP4Linear(materialize_nested_absmax=False) + group_projections: nested absmax decoded in "
+                   "the (grouped) GEMV")
         else:
             model = torch.nn.ModuleList([Block(m) for m in bnb_layers])
             model = torch_bnb_fp4.recursively_replace_with_fp4_linear(model, as_dtype=torch.bfloat16, device=dev)

@@ -171,6 +171,9 @@ void fp4_b200_layer_destroy(fp4_b200_layer_t* layer);
 fp4_b200_layer_t* fp4_b200_layer_create_grouped(int nmat, const uint8_t* const* packed, const float* const* absmax,
                                                 const float* code, const void* const* bias, const int* N, int K,
                                                 int blocksize, int dtype, unsigned flags);
+/* matrix m of a prepared group keeps its absmax double-quantised (the struct is copied; its buffers must outlive
+ * the handle); absmax[m] given at creation is then ignored */
+int fp4_b200_layer_set_nested(fp4_b200_layer_t* layer, int m, const fp4_b200_nested_t* nested);
 int fp4_b200_layer_gemv_grouped(const fp4_b200_layer_t* layer, const void* x, void* const* out, int batch,
                                 const fp4_b200_tp_t* tp, void* stream);
 
@@ -211,6 +214,9 @@ int fp4_b200_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_
 typedef struct {
     int gate_act;
     const void* const* residual;
+    /* NULL, or a HOST array of nmat pointers (entries may be NULL): matrix m carries a double-quantised absmax that
+     * is decoded in the kernel (absmax[m] is then ignored and may be NULL) */
+    const fp4_b200_nested_t* const* nested;
 } fp4_b200_epilogue_t;
 int fp4_b200_gemv_grouped_ex(const void* x, int nmat, const uint8_t* const* packed, const float* const* absmax,
                              const void* const* bias, void* const* out, const int* N, int batch, int K,

@@ -282,3 +282,24 @@ def test_fuse_gated_mlps_on_an_hf_style_block(cuda):
     x = torch.randn(2, 1024, device=cuda, dtype=torch.float16)
     y = fused.__dict__["_fp4_fused_mlp"](x, residual=res)
     assert normwise(y.float().cpu().numpy(), (plain(x).float() + res.float()).cpu().numpy()) <= 4e-3
+
+
+def test_grouped_launch_with_nested_members(cuda):
+    """q/k/v kept double-quantised (materialize_nested_absmax=False) still share one launch: the grouped kernel
+    decodes each member's nested absmax; outputs equal the members' own launches up to fp32 summation order."""
+    from torch_bnb_fp4_b200._lib import lib
+    torch.manual_seed(21)
+    ws = [(torch.randn(n, 1024) * 0.03).to(cuda) for n in (1024, 256, 256)]
+    mods = [torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w, compress_statistics=True),
+                                         materialize_nested_absmax=False) for w in ws]
+    assert all(m.quant_data.nested is not None and m.quant_data.absmax is None for m in mods)
+    grp = torch_bnb_fp4.TorchFP4LinearGroup(mods)
+    assert grp._groupable
+    for rows in (1, 4):
+        x = torch.randn(rows, 1024, device=cuda, dtype=torch.bfloat16)
+        grp(x)
+        n0 = lib.fp4_b200_launch_count()
+        outs = grp(x)
+        assert lib.fp4_b200_launch_count() - n0 == 1
+        for o, m in zip(outs, mods):
+            assert normwise(o.float().cpu().numpy(), m(x).float().cpu().numpy()) <= 8e-3

@@ -401,6 +401,27 @@ def test_gemv_stream_kernel_random_shapes(cuda):
         assert normwise(y.float().cpu().numpy(), exact) <= TOL64[dtype], (N, K, batch, dtype)
 
 
+@pytest.mark.parametrize("rows", [16, 300, 1024])
+def test_gemm_tcgen05_config5_shape(cuda, rows):
+    """BASELINE config #5: the 28672x8192 weight of the prefill sweep.  The fused GEMM against this library's dequant
+    + cuBLAS on the same inputs: both multiply the same bf16 weights and accumulate in fp32, so they agree to the
+    output rounding (on most shapes bit for bit)."""
+    N, K = 28672, 8192
+    gen = torch.Generator(device=cuda).manual_seed(rows)
+    packed = torch.randint(0, 256, (N * K // 2, 1), dtype=torch.uint8, device=cuda, generator=gen)
+    absmax = torch.rand(N * K // 64, device=cuda, generator=gen) * 0.02 + 0.01
+    x = torch.randn(rows, K, device=cuda, generator=gen).bfloat16()
+    y = ext.gemm_fp4(x, packed, absmax, _code(cuda), N, K, 64)
+    w = ext.dequantize_fp4(packed, absmax, 64, N, K, ext.bfloat16)
+    ref = torch.nn.functional.linear(x, w)
+    assert y.shape == (rows, N)
+    err = ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+    assert err <= 4e-3, err
+    # spot-check a band of rows against fp64 on the dequantised weights
+    r64 = x[:4].double() @ w[:512].double().t()
+    assert ((y[:4, :512].double() - r64).abs().max() / r64.abs().max()).item() <= 4e-3
+
+
 def test_gemm_tcgen05_random_shapes(cuda):
     rng = np.random.default_rng(77)
     for case in range(10):

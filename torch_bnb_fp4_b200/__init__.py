@@ -407,8 +407,9 @@ class TorchFP4LinearGroup(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList(layers)
         qds = [m.quant_data for m in self.layers]
-        self._groupable = (len(qds) <= 4 and all(q.nested is None and q._code_is_std and q.blocksize == 64
-                                                 for q in qds) and len({q.N for q in qds}) == 1)
+        # (a member may keep its absmax double-quantised: the kernel decodes it)
+        self._groupable = (len(qds) <= 4 and all(q._code_is_std and q.blocksize == 64 for q in qds)
+                           and len({q.N for q in qds}) == 1)
         self._launchers = {}
 
     def forward(self, x: torch.Tensor):
@@ -425,7 +426,8 @@ class TorchFP4LinearGroup(nn.Module):
                 if la is None:
                     try:
                         la = _ext.GroupLauncher([q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
-                                                [q._Bshape for q in qds], [q._bias_t for q in qds])
+                                                [q._Bshape for q in qds], [q._bias_t for q in qds],
+                                                [q.nested for q in qds])
                     except Exception:  # noqa: BLE001 - the checked path below reports it properly
                         la = False
                     self._launchers[x.dtype] = la
@@ -433,11 +435,12 @@ class TorchFP4LinearGroup(nn.Module):
                     outs = la(x, rows)
                     if outs is not None:
                         return tuple(outs)
-            xc = x if x.is_contiguous() else x.contiguous()
-            outs = _ext.gemv_fp4_grouped(xc, [q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
-                                         [q._Bshape for q in qds], [q._bias_t for q in qds])
-            if outs is not None:
-                return tuple(outs)
+            if all(q.nested is None for q in qds):
+                xc = x if x.is_contiguous() else x.contiguous()
+                outs = _ext.gemv_fp4_grouped(xc, [q.A for q in qds], [q.absmax for q in qds], 64, qds[0].qtype,
+                                             [q._Bshape for q in qds], [q._bias_t for q in qds])
+                if outs is not None:
+                    return tuple(outs)
         return tuple(m(x) for m in self.layers)
 
 
@@ -503,9 +506,30 @@ class TorchFP4GatedMLP(nn.Module):
         return y if residual is None else y + residual
 
 
+def _which_activation(fn) -> Optional[str]:
+    """'silu' / 'gelu_tanh' if `fn` computes that function (probed numerically, so nn.SiLU, F.silu and the
+    activation classes of transformers are all recognised), else None."""
+    if fn is None or not callable(fn):
+        return None
+    t = torch.linspace(-6.0, 6.0, 97)
+    try:
+        with torch.no_grad():
+            y = fn(t.clone())
+    except Exception:  # noqa: BLE001
+        return None
+    if not torch.is_tensor(y) or y.shape != t.shape:
+        return None
+    if torch.allclose(y, torch.nn.functional.silu(t), atol=1e-6, rtol=1e-5):
+        return "silu"
+    if torch.allclose(y, torch.nn.functional.gelu(t, approximate="tanh"), atol=1e-6, rtol=1e-5):
+        return "gelu_tanh"
+    return None
+
+
 def fuse_gated_mlps(model: nn.Module) -> int:
     """Opt-in: give every sub-module that looks like an HF gated MLP - TorchFP4Linear children named gate_proj /
-    up_proj / down_proj and an ``act_fn`` that is SiLU or tanh-GELU, forward = down(act(gate(x)) * up(x)) - a forward
+    up_proj / down_proj and an ``act_fn`` that computes SiLU or tanh-GELU (probed numerically), forward =
+    down(act(gate(x)) * up(x)) - a forward
     that runs through TorchFP4GatedMLP.  Returns the number of blocks fused."""
     import types
     made = 0
@@ -513,12 +537,8 @@ def fuse_gated_mlps(model: nn.Module) -> int:
         subs = [getattr(mod, n, None) for n in ("gate_proj", "up_proj", "down_proj")]
         if not all(isinstance(_unwrap(m), TorchFP4Linear) for m in subs if m is not None) or None in subs:
             continue
-        act_fn = getattr(mod, "act_fn", None)
-        if isinstance(act_fn, nn.SiLU):
-            act = "silu"
-        elif isinstance(act_fn, nn.GELU) and getattr(act_fn, "approximate", "none") == "tanh":
-            act = "gelu_tanh"
-        else:
+        act = _which_activation(getattr(mod, "act_fn", None))
+        if act is None:
             continue
         fused = TorchFP4GatedMLP(*subs, act=act)
         mod.__dict__["_fp4_fused_mlp"] = fused  # not registered: the block keeps owning its layers

@@ -22,7 +22,7 @@ EXPORTS = [
     "fp4_b200_gemv_workspace_bytes", "fp4_b200_gemv_grouped", "fp4_b200_gemv_grouped_tp", "fp4_b200_gemm",
     "fp4_b200_quantize", "fp4_b200_layer_create", "fp4_b200_layer_gemv", "fp4_b200_layer_destroy",
     "fp4_b200_layer_create_grouped", "fp4_b200_layer_gemv_grouped", "fp4_b200_launch_count",
-    "fp4_b200_gemv_grouped_ex",
+    "fp4_b200_gemv_grouped_ex", "fp4_b200_layer_set_nested",
 ]
 
 
@@ -42,7 +42,8 @@ class TpExchange(ctypes.Structure):
 
 class Epilogue(ctypes.Structure):
     """fp4_b200_epilogue_t"""
-    _fields_ = [("gate_act", ctypes.c_int), ("residual", ctypes.POINTER(ctypes.c_void_p))]
+    _fields_ = [("gate_act", ctypes.c_int), ("residual", ctypes.POINTER(ctypes.c_void_p)),
+                ("nested", ctypes.POINTER(ctypes.POINTER(Nested)))]
 
 
 GATE_ACT = {"silu": 1, "gelu_tanh": 2}
@@ -69,6 +70,7 @@ def _load() -> ctypes.CDLL:
     lib.fp4_b200_layer_destroy.argtypes = [vp]
     lib.fp4_b200_layer_create_grouped.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, ctypes.POINTER(vp),
                                                   ctypes.POINTER(i32), i32, i32, i32, u32]
+    lib.fp4_b200_layer_set_nested.argtypes = [vp, i32, ctypes.POINTER(Nested)]
     lib.fp4_b200_layer_gemv_grouped.argtypes = [vp, vp, ctypes.POINTER(vp), i32, ctypes.POINTER(TpExchange), vp]
     lib.fp4_b200_gemv_grouped.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                           ctypes.POINTER(vp), ctypes.POINTER(i32), i32, i32, i32, i32, u32, vp]

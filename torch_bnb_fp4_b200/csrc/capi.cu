@@ -144,9 +144,11 @@ int fp4_b200_gemv_grouped_ex(const void* x, int nmat, const uint8_t* const* pack
     if (dtype != FP4_B200_F16 && dtype != FP4_B200_BF16 && dtype != FP4_B200_F32) return FP4_B200_ERR_DTYPE;
     if (!(flags & FP4_B200_FLAG_CODE_IS_BNB_FP4)) return FP4_B200_ERR_UNSUPPORTED;  // bitsandbytes table only
     const bool gated = epi && epi->gate_act;
-    for (int m = 0; m < nmat; ++m)
-        if (!packed[m] || !absmax[m] || (!out[m] && !(tp && tp->out_world > 1) && !(gated && m == 1)))
+    for (int m = 0; m < nmat; ++m) {
+        const bool nested_m = epi && epi->nested && epi->nested[m];
+        if (!packed[m] || (!absmax[m] && !nested_m) || (!out[m] && !(tp && tp->out_world > 1) && !(gated && m == 1)))
             return FP4_B200_ERR_NULL;
+    }
     if (x && reinterpret_cast<uintptr_t>(x) % 16) return FP4_B200_ERR_ALIGN;
     if (tp) {
         if (tp->in_world < 0 || tp->in_world > 8 || tp->out_world < 0 || tp->out_world > 8) return FP4_B200_ERR_SHAPE;
@@ -184,6 +186,8 @@ size_t fp4_b200_gemv_workspace_bytes(int N) {
 }
 
 struct fp4_b200_layer {
+    fp4_b200_nested_t nested[4];
+    const fp4_b200_nested_t* pnested[4];  // NULL, or &nested[m]
     int nmat;
     const uint8_t* packed[4];
     const float* absmax[4];
@@ -202,7 +206,7 @@ fp4_b200_layer_t* fp4_b200_layer_create_grouped(int nmat, const uint8_t* const* 
     if (!l) return nullptr;
     l->nmat = nmat;
     for (int m = 0; m < nmat; ++m) {
-        if (!packed[m] || !absmax[m] || N[m] <= 0) { delete l; return nullptr; }
+        if (!packed[m] || N[m] <= 0) { delete l; return nullptr; }  // (absmax[m] may be NULL until set_nested)
         l->packed[m] = packed[m]; l->absmax[m] = absmax[m]; l->bias[m] = bias ? bias[m] : nullptr; l->N[m] = N[m];
     }
     l->code = code; l->K = K; l->blocksize = blocksize; l->dtype = dtype; l->flags = flags;
@@ -215,12 +219,20 @@ fp4_b200_layer_t* fp4_b200_layer_create(const uint8_t* packed, const float* absm
     return fp4_b200_layer_create_grouped(1, &packed, &absmax, code, &bias, &N, K, blocksize, dtype, flags);
 }
 
+int fp4_b200_layer_set_nested(fp4_b200_layer_t* l, int m, const fp4_b200_nested_t* nested) {
+    if (!l || !nested) return FP4_B200_ERR_NULL;
+    if (m < 0 || m >= l->nmat) return FP4_B200_ERR_SHAPE;
+    l->nested[m] = *nested;
+    l->pnested[m] = &l->nested[m];
+    return FP4_B200_OK;
+}
+
 int fp4_b200_layer_gemv(const fp4_b200_layer_t* lc, const void* x, void* out, int batch, void* workspace,
                         size_t workspace_bytes, void* stream) {
     if (!lc) return FP4_B200_ERR_NULL;
     if (lc->nmat != 1) return FP4_B200_ERR_SHAPE;
     const fp4_b200_layer* l = lc;
-    return fp4_b200_gemv(x, l->packed[0], l->absmax[0], nullptr, l->code, l->bias[0], out, batch, l->N[0], l->K,
+    return fp4_b200_gemv(x, l->packed[0], l->absmax[0], l->pnested[0], l->code, l->bias[0], out, batch, l->N[0], l->K,
                          l->blocksize, l->dtype, l->flags, workspace, workspace_bytes, stream);
 }
 
@@ -228,8 +240,12 @@ int fp4_b200_layer_gemv_grouped(const fp4_b200_layer_t* lc, const void* x, void*
                                 const fp4_b200_tp_t* tp, void* stream) {
     if (!lc || !out) return FP4_B200_ERR_NULL;
     const fp4_b200_layer* l = lc;
-    return fp4_b200_gemv_grouped_tp(x, l->nmat, l->packed, l->absmax, l->bias, out, l->N, batch, l->K, l->blocksize,
-                                    l->dtype, l->flags, tp, stream);
+    fp4_b200_epilogue_t epi = {};
+    bool any = false;
+    for (int m = 0; m < l->nmat; ++m) any = any || l->pnested[m];
+    epi.nested = any ? l->pnested : nullptr;
+    return fp4_b200_gemv_grouped_ex(x, l->nmat, l->packed, l->absmax, l->bias, out, l->N, batch, l->K, l->blocksize,
+                                    l->dtype, l->flags, tp, any ? &epi : nullptr, stream);
 }
 
 void fp4_b200_layer_destroy(fp4_b200_layer_t* l) { delete l; }

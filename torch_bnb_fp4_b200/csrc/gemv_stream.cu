@@ -1073,7 +1073,7 @@ bool gemv_stream_group_supported(int nmat, int batch, const int* N, int K, int b
     long total = 0;
     for (int m = 0; m < nmat; ++m) {
         if (N[m] <= 0 || N[m] % 16 != 0) return false;
-        if (reinterpret_cast<uintptr_t>(packed[m]) % 16 || reinterpret_cast<uintptr_t>(absmax[m]) % 16) return false;
+        if (reinterpret_cast<uintptr_t>(packed[m]) % 16 || reinterpret_cast<uintptr_t>(absmax[m]) % 16) return false;  // (NULL passes)
         total += N[m];
     }
     if (total > (1 << 24)) return false;
@@ -1091,10 +1091,13 @@ int gemv_stream_group_dispatch(const void* x, int nmat, const uint8_t* const* pa
         gr.packed[m] = packed[m]; gr.absmax[m] = absmax[m]; gr.bias[m] = bias ? bias[m] : nullptr;
         gr.out[m] = out[m]; gr.N[m] = N[m];
         gr.residual[m] = (epi && epi->residual) ? epi->residual[m] : nullptr;
+        gr.nested[m] = (epi && epi->nested) ? epi->nested[m] : nullptr;
+        if (!nested_ok(gr.nested[m])) return FP4_B200_ERR_UNSUPPORTED;
     }
     if (epi && epi->gate_act) {
         const bool tp_on = tp && (tp->in_world > 1 || tp->out_world > 1);
-        if (nmat != 2 || N[0] != N[1] || N[0] % 8 || epi->gate_act < 1 || epi->gate_act > 2 || tp_on || epi->residual)
+        if (nmat != 2 || N[0] != N[1] || N[0] % 8 || epi->gate_act < 1 || epi->gate_act > 2 || tp_on || epi->residual ||
+            gr.nested[0] || gr.nested[1])
             return FP4_B200_ERR_UNSUPPORTED;
         gr.gated = epi->gate_act;
     }

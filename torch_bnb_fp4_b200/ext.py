@@ -430,7 +430,9 @@ class GroupLauncher:
     __slots__ = ("keep", "n", "pk", "am", "bi", "ou", "ns", "n_outs", "k", "blocksize", "dt", "dtcode", "dev",
                  "idx", "unsupported", "handle")
 
-    def __init__(self, Bs, absmaxes, blocksize, dtype, Bshapes, biases=None):
+    def __init__(self, Bs, absmaxes, blocksize, dtype, Bshapes, biases=None, nesteds=None):
+        """absmaxes[i] may be None when nesteds[i] (a _lib.Nested from make_nested) is given: that member keeps its
+        absmax double-quantised and the kernel decodes it."""
         self.dt = get_scalar_type(dtype)
         n = self.n = len(Bs)
         if n < 1 or n > 4 or len(absmaxes) != n or len(Bshapes) != n:
@@ -438,13 +440,15 @@ class GroupLauncher:
         self.k = int(Bshapes[0][1])
         if any(int(sh[1]) != self.k for sh in Bshapes):
             raise RuntimeError("grouped GEMV: every weight must have the same in_features")
-        for B, a in zip(Bs, absmaxes):
+        nesteds = list(nesteds) if nesteds is not None else [None] * n
+        for B, a, nd in zip(Bs, absmaxes, nesteds):
             _check_in(B, "B", torch.uint8)
-            _check_in(a, "absmax", torch.float32)
+            if nd is None:
+                _check_in(a, "absmax", torch.float32)
         vp = ctypes.c_void_p
         self.n_outs = [int(sh[0]) for sh in Bshapes]
         self.pk = (vp * n)(*[B.data_ptr() for B in Bs])
-        self.am = (vp * n)(*[a.data_ptr() for a in absmaxes])
+        self.am = (vp * n)(*[None if a is None else a.data_ptr() for a in absmaxes])
         self.ou = (vp * n)()
         self.ns = (ctypes.c_int * n)(*self.n_outs)
         self.bi = None
@@ -453,7 +457,7 @@ class GroupLauncher:
                 if b is not None:
                     _check_in(b, "bias", self.dt)
             self.bi = (vp * n)(*[None if b is None else b.data_ptr() for b in biases])
-        self.keep = (list(Bs), list(absmaxes), None if biases is None else list(biases))
+        self.keep = (list(Bs), list(absmaxes), None if biases is None else list(biases), nesteds)
         self.blocksize, self.dtcode = int(blocksize), _CODE_OF[self.dt]
         self.dev, self.idx = Bs[0].device, Bs[0].device.index
         self.unsupported = set()  # batch sizes the grouped kernel refused (FP4_B200_ERR_UNSUPPORTED)
@@ -462,6 +466,9 @@ class GroupLauncher:
                                                         self.blocksize, self.dtcode, _lib.FLAG_CODE_IS_BNB_FP4)
         if not self.handle:
             raise RuntimeError("fp4_b200_layer_create_grouped failed")
+        for i, nd in enumerate(nesteds):
+            if nd is not None:
+                check(lib.fp4_b200_layer_set_nested(self.handle, i, ctypes.byref(nd)), "fp4_b200_layer_set_nested")
 
     def __del__(self):
         try:
