@@ -94,9 +94,14 @@ typedef struct {
  *   consumer:  in_world > 1, in_base = this rank's exchange buffer;
  *   producer:  out_world > 1, out_peer_base[q] = rank q's exchange buffer as mapped on this GPU (the call's
  *              out[0] is ignored), out_rank = this rank.
- * epochs: two uint32 in local device memory, zero-initialised: [0] = last epoch published by this rank's
- * producers, [1] = last epoch its consumers finished.  Every rank must issue the same sequence of calls, and a
- * published partial must be consumed before the next one is published.  err is set to 1 if a wait gave up. */
+ * epochs: two uint32 in local device memory, zero-initialised: [1] = last epoch this rank's consumers finished
+ * (the exchange epoch of a producer and of the consumer after it is epochs[1] + 1; [0] is reserved).  Every rank
+ * must issue the same sequence of calls, and a published partial must be consumed - by exactly one consumer launch -
+ * before the next one is published.
+ * A consumer launch with x == NULL does NOT wait for the preceding kernels of its stream (its input validates
+ * itself word by word, so it polls while the producers are still running); its bias and output buffers must
+ * therefore not be written or read by the kernel directly before it.  A wait that gets no data for 20 s sets err
+ * to 1 and traps. */
 typedef struct {
     int in_world;
     const void* in_base;

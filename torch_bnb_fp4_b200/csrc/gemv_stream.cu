@@ -319,9 +319,18 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     };
     loader_at(ld_gt, ku_a);
     TL_STAMP(0);
+    // tensor parallel (see the helpers above): a PRODUCER pushes its output into every rank's exchange buffer, a
+    // CONSUMER's x is the sum of the ranks' partials read out of its own exchange buffer
+    const int in_world = EXTRA ? p.tp.in_world : 0, out_world = EXTRA ? p.tp.out_world : 0;
+    const bool producer = out_world > 1;
+    // a consumer that reads nothing but the exchange needs no grid dependency at all: every word it reads validates
+    // itself, so it starts polling while the producer (of this and of the other ranks) is still running - no
+    // completion -> release latency, no wait for the slowest CTA.  The producer in turn lets its dependents start
+    // only AFTER its own wait, so a consumer never overtakes the kernels before its producer.
+    const bool free_running = EXTRA && in_world > 1 && !producer && p.x == nullptr;
     // the next kernel of the stream may be scheduled as soon as every CTA of this one is running: its CTAs then
     // start (and request their first ring slot) the moment a CTA of this kernel leaves its SM
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (!producer) asm volatile("griddepcontrol.launch_dependents;");
     uint32_t ld_ku = ku_a, issued = 0;
     // copy the next unit of this warp's range into ring slot `dst` (lane-private bytes) and advance
     // (steps [j0, j1) of the unit; the absmax rides with step 0, the loader advances after step 3)
@@ -363,16 +372,18 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     if (p.pre >= 4) cp_async_commit();  // one group per slot, empty or not: the number of pending groups stays `ring`
     TL_STAMP(1);
     // x and `out` may be products of the previous kernel: wait for it
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!free_running) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (producer) asm volatile("griddepcontrol.launch_dependents;");
     TL_STAMP(2);
-    // tensor parallel (see the helpers above).  Epochs: [0] = last published by this rank's producers,
-    // [1] = last finished by its consumers; both only change between the kernels that read them.
-    const int in_world = EXTRA ? p.tp.in_world : 0, out_world = EXTRA ? p.tp.out_world : 0;
+    // Epoch of the exchange = epochs[1] + 1, where epochs[1] is the last epoch this rank's consumers finished: a
+    // producer publishes it, the consumer after it consumes it and advances epochs[1] when it ends.  The word is
+    // written by the previous consumer, which completed before the producer passed its wait, i.e. before either
+    // kernel of the current pair started.
     uint32_t in_tag = 0, out_tag = 0, e_in = 0, e_out = 0;
     const uint8_t* in_slot = nullptr;
     size_t out_off = 0;
     if (in_world > 1) {
-        e_in = __ldcg(p.tp.epochs);
+        e_in = __ldcg(p.tp.epochs + 1) + 1u;
         in_tag = e_in & 0xFFFFu;
         in_slot = reinterpret_cast<const uint8_t*>(p.tp.in_base) + (size_t)(e_in & 1u) * in_world * p.tp.slot_bytes;
     }
@@ -840,7 +851,6 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     }
     // epoch bookkeeping for the NEXT kernel of this stream (kernel boundaries order these plain stores)
     if (blockIdx.x == 0 && tid == 0) {
-        if (out_world > 1) *reinterpret_cast<volatile uint32_t*>(p.tp.epochs) = e_out;
         if (in_world > 1) *reinterpret_cast<volatile uint32_t*>(p.tp.epochs + 1) = e_in;
     }
     TL_STAMP(7);
