@@ -27,3 +27,25 @@ def test_peer_exchange_two_ranks():
     skew = re.findall(r"skewed ranks, batch 1\.\.8: peer vs nccl worst ([0-9.e+-]+)", out)
     assert len(skew) == 2 and all(float(v) <= 3e-2 for v in skew), out
     assert len(re.findall(r"graph replay vs eager 0\.00e\+00", out)) == 2
+
+
+@pytest.mark.gpu
+def test_one_process_two_devices():
+    """the opt-in to large dynamic shared memory is per device; a process that drives two GPUs (accelerate's
+    device_map) must be able to launch every kernel on both."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import torch_bnb_fp4
+    from torch_bnb_fp4_b200 import bnb_compat
+    torch.manual_seed(0)
+    w = torch.randn(1024, 2048) * 0.03
+    for idx in (0, 1, 0):
+        dev = torch.device("cuda", idx)
+        m = torch_bnb_fp4.TorchFP4Linear(bnb_compat.make_quantized_linear(w.to(dev)))
+        for rows in (1, 6, 64, 1500):
+            x = torch.randn(rows, 2048, device=dev, dtype=torch.bfloat16)
+            y = m(x)
+            ref = torch.nn.functional.linear(x.float(), m.quant_data.dequantize().float())
+            assert y.device == dev
+            assert ((y.float() - ref).abs().max() / ref.abs().max()).item() <= 8e-3, (idx, rows)

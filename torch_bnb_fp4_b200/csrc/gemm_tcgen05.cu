@@ -814,16 +814,21 @@ static int launch_pair(const void* x, const uint8_t* packed, const float* absmax
     const size_t smem = (size_t)stagesB * kStageB + kWSlots * kWBox + kStagesA * 16 + stagesB * 24 + 32 + kWSlots * 16 +
                         64 + 1024;
     auto kern = gemm_fp4_tcgen05_pair_kernel<T>;
-    static bool configured = false;
-    static uint32_t* gfailed = nullptr;
-    if (!configured) {
+    // per device: the function attributes and the failure flag live in the device's context
+    static PerDeviceOnce configured;
+    static uint32_t* gfailed_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return FP4_B200_ERR_UNSUPPORTED;
+    if (!configured.flag()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (cudaMalloc(&gfailed, 4) != cudaSuccess) return FP4_B200_ERR_UNSUPPORTED;
-        cudaMemset(gfailed, 0, 4);
-        configured = true;
+        if (cudaMalloc(&gfailed_dev[dev], 4) != cudaSuccess) return FP4_B200_ERR_UNSUPPORTED;
+        cudaMemset(gfailed_dev[dev], 0, 4);
+        configured.flag() = true;
     }
+    uint32_t* gfailed = gfailed_dev[dev];
     Params p;
     p.packed = packed; p.absmax = absmax; p.bias = bias; p.out = out;
     p.M = M; p.N = N; p.K = K; p.bs_shift = bs_shift;
