@@ -258,7 +258,11 @@ class QuantData:
             A2 = A.reshape(rows, k)
             if not A2.is_contiguous():
                 A2 = A2.contiguous()
-            y = torch.cat([self._qgemv(A2[:GEMV_MAX_BATCH]), self._qgemv(A2[GEMV_MAX_BATCH:])], dim=0)
+            f = self._fast  # the pre-validated launcher where there is one (the checked path costs ~20 us per call)
+            if (f is not None and A2.dtype is self.o_type and A2.device.index == self._fast_idx == torch.cuda.current_device()):
+                y = torch.cat([f(A2[:GEMV_MAX_BATCH], GEMV_MAX_BATCH), f(A2[GEMV_MAX_BATCH:], rows - GEMV_MAX_BATCH)], dim=0)
+            else:
+                y = torch.cat([self._qgemv(A2[:GEMV_MAX_BATCH]), self._qgemv(A2[GEMV_MAX_BATCH:])], dim=0)
             return y.view(A.shape[:-1] + (self.M,))
         if rows <= GEMM_MAX_ROWS and gemm_ok:
             if not A.is_contiguous():
