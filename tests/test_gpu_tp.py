@@ -27,6 +27,8 @@ def test_peer_exchange_two_ranks():
     skew = re.findall(r"skewed ranks, batch 1\.\.8: peer vs nccl worst ([0-9.e+-]+)", out)
     assert len(skew) == 2 and all(float(v) <= 3e-2 for v in skew), out
     assert len(re.findall(r"graph replay vs eager 0\.00e\+00", out)) == 2
+    wrap = re.findall(r"after (\d+) epochs: batch 8 peer vs nccl ([0-9.e+-]+)", out)
+    assert len(wrap) == 2 and all(int(e) > 65536 and float(v) <= 3e-2 for e, v in wrap), out
 
 
 @pytest.mark.gpu

@@ -186,11 +186,14 @@ __device__ __forceinline__ float gate_act(float v, int kind) {
 }
 
 // ---- tensor-parallel exchange through peer (symmetric) memory -------------------------------------------
-// A row-parallel layer pushes its partial output, as self-validating 32-bit words {value16, tag16 = epoch},
-// into every rank's exchange buffer over NVLink (no fences, no flags); the consumer sums the ranks' partials
-// out of its LOCAL buffer while it stages x, re-reading words whose tag is not the current epoch yet.
-__device__ __forceinline__ void st_peer_u32(void* p, uint32_t v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// A row-parallel layer pushes its partial output, as self-validating 64-bit words {fp32 value, tag32 = epoch},
+// into every rank's exchange buffer over NVLink (no fences, no flags: an aligned 8-byte store is single-copy
+// atomic); the consumer sums the ranks' partials (in fp32, fixed rank order) out of its LOCAL buffer while it
+// stages x, re-reading words whose tag is not the current epoch yet.  A 32-bit tag does not come round again in
+// the life of a process (2^32 epochs = tens of millions of tokens), so a word left over from another batch size can
+// never validate by accident (the 16-bit tags of round 1 aliased after 65536 epochs).
+__device__ __forceinline__ void st_peer_word(void* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
 __device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by other GPUs: never the read-only path
     uint4 r;
@@ -200,40 +203,19 @@ __device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by othe
                  : "memory");
     return r;
 }
-template <typename T>
-__device__ __forceinline__ float tp_word_value(uint32_t w) {
-    if constexpr (sizeof(T) == 2 && DT<T>::code == FP4_B200_BF16) {
-        return __uint_as_float(w << 16);
-    } else {
-        return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
-    }
-}
-template <typename T>
-__device__ __forceinline__ uint32_t tp_word(float v, uint32_t tag) {
-    unsigned short h;
-    if constexpr (sizeof(T) == 2 && DT<T>::code == FP4_B200_BF16) {
-        h = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-    } else {
-        h = __half_as_ushort(__float2half_rn(v));
-    }
-    return (uint32_t)h | (tag << 16);
-}
 // 8 consecutive elements of rank `r`'s partial for the epoch with tag `tag`; waits for late words.  A peer that
 // has not delivered after kTpTimeoutNs (a dead rank, or call sequences that diverged) is fatal: the flag is
 // raised for the host and the kernel traps instead of computing with unvalidated words.
 constexpr unsigned long long kTpTimeoutNs = 20ull * 1000 * 1000 * 1000;
-template <typename T>
 __device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float (&f)[8], uint32_t* err) {
     unsigned long long t0 = 0;
     for (uint32_t spins = 0;; ++spins) {
-        const uint4 a = ld_peer_u4(src), b = ld_peer_u4(src + 16);
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ok = ok && (w[i] >> 16) == tag;
+        const uint4 a = ld_peer_u4(src), b = ld_peer_u4(src + 16), c = ld_peer_u4(src + 32), d = ld_peer_u4(src + 48);
+        const bool ok = a.y == tag && a.w == tag && b.y == tag && b.w == tag && c.y == tag && c.w == tag &&
+                        d.y == tag && d.w == tag;
         if (ok) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = tp_word_value<T>(w[i]);
+            f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.z); f[2] = __uint_as_float(b.x); f[3] = __uint_as_float(b.z);
+            f[4] = __uint_as_float(c.x); f[5] = __uint_as_float(c.z); f[6] = __uint_as_float(d.x); f[7] = __uint_as_float(d.z);
             return;
         }
         if ((spins & 4095u) == 4095u) {
@@ -384,12 +366,12 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
     size_t out_off = 0;
     if (in_world > 1) {
         e_in = __ldcg(p.tp.epochs + 1) + 1u;
-        in_tag = e_in & 0xFFFFu;
+        in_tag = e_in;
         in_slot = reinterpret_cast<const uint8_t*>(p.tp.in_base) + (size_t)(e_in & 1u) * in_world * p.tp.slot_bytes;
     }
     if (out_world > 1) {
         e_out = __ldcg(p.tp.epochs + 1) + 1u;
-        out_tag = e_out & 0xFFFFu;
+        out_tag = e_out;
         out_off = ((size_t)(e_out & 1u) * out_world + p.tp.out_rank) * p.tp.slot_bytes;
     }
 
@@ -455,20 +437,18 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             }
         };
         if (in_world > 1) {
-            if constexpr (sizeof(T) == 2) {
-                for (int b = 0; b < batch; ++b) {
-                    for (int c = tid; c < nchunk; c += kThreads) {
-                        float f[8];
-                        const size_t off = ((size_t)b * K + (size_t)c * 8) * 4;
-                        tp_load8<T>(in_slot + off, in_tag, f, p.tp.err);
-                        for (int r = 1; r < in_world; ++r) {  // fixed rank order: every rank computes the same x
-                            float fr[8];
-                            tp_load8<T>(in_slot + (size_t)r * p.tp.slot_bytes + off, in_tag, fr, p.tp.err);
+            for (int b = 0; b < batch; ++b) {
+                for (int c = tid; c < nchunk; c += kThreads) {
+                    float f[8];
+                    const size_t off = ((size_t)b * K + (size_t)c * 8) * 8;
+                    tp_load8(in_slot + off, in_tag, f, p.tp.err);
+                    for (int r = 1; r < in_world; ++r) {  // fixed rank order: every rank computes the same x
+                        float fr[8];
+                        tp_load8(in_slot + (size_t)r * p.tp.slot_bytes + off, in_tag, fr, p.tp.err);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] += fr[i];
-                        }
-                        stage_chunk(b, c, f);
+                        for (int i = 0; i < 8; ++i) f[i] += fr[i];
                     }
+                    stage_chunk(b, c, f);
                 }
             }
         } else {
@@ -620,13 +600,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                         v1 += DT<T>::to_f32(res[(size_t)b * Nm + r1]);
                     }
                     if (out_world > 1) {
-                        if constexpr (sizeof(T) == 2) {
-                            const uint32_t w0 = tp_word<T>(v0, out_tag), w1 = tp_word<T>(v1, out_tag);
-                            for (int q = 0; q < out_world; ++q) {
-                                uint8_t* dst = reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off;
-                                st_peer_u32(dst + ((size_t)b * Nm + r0) * 4, w0);
-                                st_peer_u32(dst + ((size_t)b * Nm + r1) * 4, w1);
-                            }
+                        for (int q = 0; q < out_world; ++q) {
+                            uint8_t* dst = reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off;
+                            st_peer_word(dst + ((size_t)b * Nm + r0) * 8, v0, out_tag);
+                            st_peer_word(dst + ((size_t)b * Nm + r1) * 8, v1, out_tag);
                         }
                     } else {
                         out[(size_t)b * Nm + r0] = DT<T>::from_f32(v0);
@@ -838,12 +815,9 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             if (bias) v += DT<T>::to_f32(bias[row]);
             if (EXTRA && p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
             if (out_world > 1) {
-                if constexpr (sizeof(T) == 2) {
-                    const uint32_t w_ = tp_word<T>(v, out_tag);
-                    for (int q = 0; q < out_world; ++q)
-                        st_peer_u32(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off +
-                                        ((size_t)b * p.Nm[mm] + row) * 4, w_);
-                }
+                for (int q = 0; q < out_world; ++q)
+                    st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off +
+                                     ((size_t)b * p.Nm[mm] + row) * 8, v, out_tag);
             } else {
                 reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
             }
