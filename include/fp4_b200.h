@@ -83,14 +83,17 @@ typedef struct {
     int blocksize2;          /* state2.blocksize (256 in bitsandbytes)        */
 } fp4_b200_nested_t;
 
-/* Tensor-parallel exchange through peer (symmetric) memory, for fp4_b200_gemv_grouped_tp.
+/* Tensor-parallel exchange through peer (symmetric) memory, for fp4_b200_gemv_grouped_tp (16-bit dtypes).
  * A row-parallel layer (o / down projection) produces PARTIAL sums.  Instead of a collective launch it PUSHES
- * them, element by element as 64-bit words {fp32 value, tag32 = epoch}, into the exchange buffer of every rank
- * (plain 8-byte NVLink stores, no fences, no flags: each word validates itself, as in NCCL's LL protocol); the
- * consumer - the next column-parallel layer - reads only its LOCAL buffer while it stages x, re-reading words
- * whose tag is not yet the current epoch, and sums the ranks' partials in fp32 in rank order.
+ * them, as 64-bit words {two 16-bit values, tag32 = epoch}, into the exchange buffer of every rank (plain 8-byte
+ * NVLink stores, no fences, no flags: each word validates itself, as in NCCL's LL protocol); the consumer - the
+ * next column-parallel layer - reads only its LOCAL buffer while it stages x, re-reading words whose tag is not
+ * yet the current epoch, and sums the ranks' partials in fp32 in rank order.  The 32-bit tag does not come round
+ * again in the life of a process, so a word left over from an earlier, larger batch can never validate.
  * Exchange buffer of a rank: [2 slots (epoch parity)][world][slot_bytes / 8 words]; rank r's partial for epoch e
- * lives at word offset ((e & 1) * world + r) * slot_bytes / 8 + (b * N + row).  Must start zero-filled.
+ * starts at word ((e & 1) * world + r) * slot_bytes / 8; within it the word (b * N + (row & ~15)) / 2 + (row & 7)
+ * carries output rows `row` (bit 3 clear, low half) and `row + 8` (high half) of batch row b: N % 16 == 0,
+ * batch * N * 4 <= slot_bytes.  Must start zero-filled.
  *   consumer:  in_world > 1, in_base = this rank's exchange buffer;
  *   producer:  out_world > 1, out_peer_base[q] = rank q's exchange buffer as mapped on this GPU (the call's
  *              out[0] is ignored), out_rank = this rank.

@@ -1,2 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_hf.py -q -m gpu 2>&1 | tail -4
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/tp_fused_check.py > gpurun_out/r02_tp_fused_check.log 2>&1
+grep -v Warning gpurun_out/r02_tp_fused_check.log | grep "rank 0\|rank 1" | grep -v "done\|ready\|built" | tail -12
 bash tools/run_tp.sh 2

@@ -156,8 +156,9 @@ int fp4_b200_gemv_grouped_ex(const void* x, int nmat, const uint8_t* const* pack
         if (on && (!tp->epochs || !tp->err || tp->slot_bytes % 16)) return FP4_B200_ERR_NULL;
         if (tp->in_world > 1 && !tp->in_base) return FP4_B200_ERR_NULL;
         if (tp->out_world > 1 && nmat != 1) return FP4_B200_ERR_SHAPE;
-        if (tp->in_world > 1 && (size_t)batch * K * 8 > tp->slot_bytes) return FP4_B200_ERR_SHAPE;  // 8-byte words
-        if (tp->out_world > 1 && (size_t)batch * N[0] * 8 > tp->slot_bytes) return FP4_B200_ERR_SHAPE;
+        if (on && dtype == FP4_B200_F32) return FP4_B200_ERR_UNSUPPORTED;  // words carry two 16-bit values
+        if (tp->in_world > 1 && (size_t)batch * K * 4 > tp->slot_bytes) return FP4_B200_ERR_SHAPE;  // 8-byte words, 2 rows each
+        if (tp->out_world > 1 && (size_t)batch * N[0] * 4 > tp->slot_bytes) return FP4_B200_ERR_SHAPE;
     }
     if (!gemv_stream_group_supported(nmat, batch, N, K, blocksize, dtype, packed, absmax))
         return FP4_B200_ERR_UNSUPPORTED;

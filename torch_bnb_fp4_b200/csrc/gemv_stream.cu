@@ -186,14 +186,34 @@ __device__ __forceinline__ float gate_act(float v, int kind) {
 }
 
 // ---- tensor-parallel exchange through peer (symmetric) memory -------------------------------------------
-// A row-parallel layer pushes its partial output, as self-validating 64-bit words {fp32 value, tag32 = epoch},
-// into every rank's exchange buffer over NVLink (no fences, no flags: an aligned 8-byte store is single-copy
-// atomic); the consumer sums the ranks' partials (in fp32, fixed rank order) out of its LOCAL buffer while it
-// stages x, re-reading words whose tag is not the current epoch yet.  A 32-bit tag does not come round again in
-// the life of a process (2^32 epochs = tens of millions of tokens), so a word left over from another batch size can
-// never validate by accident (the 16-bit tags of round 1 aliased after 65536 epochs).
-__device__ __forceinline__ void st_peer_word(void* p, float v, uint32_t tag) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+// A row-parallel layer pushes its partial output as self-validating 64-bit words {two 16-bit values, tag32 = epoch}
+// into every rank's exchange buffer over NVLink (no fences, no flags: an aligned 8-byte store is single-copy atomic);
+// the consumer sums the ranks' partials (fp32, fixed rank order) out of its LOCAL buffer while it stages x, re-reading
+// words whose tag is not the current epoch yet.  A word carries rows r and r + 8 of one 16-row tile - the two values a
+// lane of the m16n8 accumulator owns - so the producer issues ONE store per lane and rank, and the exchange moves
+// 4 bytes per element, as many as the {value16, tag16} words of round 1 whose tags came round again after 65536 epochs
+// (a word left over from a larger batch could then validate by accident).  32-bit tags do not wrap in the life of a
+// process.  Word index of (batch row b, output row r): (b * N + (r & ~15)) / 2 + (r & 7); low half: rows with bit 3 clear.
+template <typename T>
+__device__ __forceinline__ uint32_t tp_pack2(float lo, float hi) {
+    if constexpr (DT<T>::code == FP4_B200_BF16) {
+        return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+    } else {
+        return (uint32_t)__half_as_ushort(__float2half_rn(lo)) | ((uint32_t)__half_as_ushort(__float2half_rn(hi)) << 16);
+    }
+}
+template <typename T>
+__device__ __forceinline__ float tp_lo(uint32_t w) {
+    if constexpr (DT<T>::code == FP4_B200_BF16) return __uint_as_float(w << 16);
+    else return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
+}
+template <typename T>
+__device__ __forceinline__ float tp_hi(uint32_t w) {
+    if constexpr (DT<T>::code == FP4_B200_BF16) return __uint_as_float(w & 0xFFFF0000u);
+    else return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+__device__ __forceinline__ void st_peer_word(void* p, uint32_t v, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(tag) : "memory");
 }
 __device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by other GPUs: never the read-only path
     uint4 r;
@@ -203,21 +223,15 @@ __device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by othe
                  : "memory");
     return r;
 }
-// 8 consecutive elements of rank `r`'s partial for the epoch with tag `tag`; waits for late words.  A peer that
-// has not delivered after kTpTimeoutNs (a dead rank, or call sequences that diverged) is fatal: the flag is
-// raised for the host and the kernel traps instead of computing with unvalidated words.
+// Four words (a, b: two each) of one rank's partial must carry `tag`; late words are re-read.  A peer that has not
+// delivered after kTpTimeoutNs (a dead rank, or call sequences that diverged) is fatal: the flag is raised for the
+// host and the kernel traps instead of computing with unvalidated words.
 constexpr unsigned long long kTpTimeoutNs = 20ull * 1000 * 1000 * 1000;
-__device__ __forceinline__ void tp_load8(const uint8_t* src, uint32_t tag, float (&f)[8], uint32_t* err) {
+__device__ __forceinline__ void tp_wait4(const uint8_t* src, uint32_t tag, uint4& a, uint4& b, uint32_t* err) {
     unsigned long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        const uint4 a = ld_peer_u4(src), b = ld_peer_u4(src + 16), c = ld_peer_u4(src + 32), d = ld_peer_u4(src + 48);
-        const bool ok = a.y == tag && a.w == tag && b.y == tag && b.w == tag && c.y == tag && c.w == tag &&
-                        d.y == tag && d.w == tag;
-        if (ok) {
-            f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.z); f[2] = __uint_as_float(b.x); f[3] = __uint_as_float(b.z);
-            f[4] = __uint_as_float(c.x); f[5] = __uint_as_float(c.z); f[6] = __uint_as_float(d.x); f[7] = __uint_as_float(d.z);
-            return;
-        }
+    for (uint32_t spins = 0; !(a.y == tag && a.w == tag && b.y == tag && b.w == tag); ++spins) {
+        a = ld_peer_u4(src);
+        b = ld_peer_u4(src + 16);
         if ((spins & 4095u) == 4095u) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -437,18 +451,44 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             }
         };
         if (in_world > 1) {
-            for (int b = 0; b < batch; ++b) {
-                for (int c = tid; c < nchunk; c += kThreads) {
-                    float f[8];
-                    const size_t off = ((size_t)b * K + (size_t)c * 8) * 8;
-                    tp_load8(in_slot + off, in_tag, f, p.tp.err);
-                    for (int r = 1; r < in_world; ++r) {  // fixed rank order: every rank computes the same x
-                        float fr[8];
-                        tp_load8(in_slot + (size_t)r * p.tp.slot_bytes + off, in_tag, fr, p.tp.err);
+            if constexpr (sizeof(T) == 2) {
+                // thread c reads words 4c..4c+3 of each rank (the loads of up to four ranks in flight together): rows
+                // 16*(c/2) + 4*(c&1) + i in the low halves and those 8 further in the high halves; lane pairs then swap
+                // what the other needs, so the even lane holds chunk c and the odd lane chunk c of x as usual
+                for (int b = 0; b < batch; ++b) {
+                    for (int c = tid; c < nchunk; c += kThreads) {
+                        const uint8_t* src = in_slot + ((size_t)b * (K >> 1) + (size_t)c * 4) * 8;
+                        float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int r0 = 0; r0 < in_world; r0 += 4) {
+                            uint4 wa[4], wb[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] += fr[i];
+                            for (int j = 0; j < 4; ++j) {
+                                if (r0 + j < in_world) {
+                                    wa[j] = ld_peer_u4(src + (size_t)(r0 + j) * p.tp.slot_bytes);
+                                    wb[j] = ld_peer_u4(src + (size_t)(r0 + j) * p.tp.slot_bytes + 16);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {  // fixed rank order: every rank computes the same x
+                                if (r0 + j < in_world) {
+                                    tp_wait4(src + (size_t)(r0 + j) * p.tp.slot_bytes, in_tag, wa[j], wb[j], p.tp.err);
+                                    lo[0] += tp_lo<T>(wa[j].x); hi[0] += tp_hi<T>(wa[j].x);
+                                    lo[1] += tp_lo<T>(wa[j].z); hi[1] += tp_hi<T>(wa[j].z);
+                                    lo[2] += tp_lo<T>(wb[j].x); hi[2] += tp_hi<T>(wb[j].x);
+                                    lo[3] += tp_lo<T>(wb[j].z); hi[3] += tp_hi<T>(wb[j].z);
+                                }
+                            }
+                        }
+                        const bool odd = c & 1;
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float got = __shfl_xor_sync(0xffffffffu, odd ? lo[i] : hi[i], 1);
+                            f[i] = odd ? got : lo[i];      // even lane: rows 0..3 its own, 4..7 the odd lane's low halves
+                            f[i + 4] = odd ? hi[i] : got;  // odd lane: rows 8..11 the even lane's high halves, 12..15 its own
+                        }
+                        stage_chunk(b, c, f);
                     }
-                    stage_chunk(b, c, f);
                 }
             }
         } else {
@@ -600,10 +640,11 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                         v1 += DT<T>::to_f32(res[(size_t)b * Nm + r1]);
                     }
                     if (out_world > 1) {
-                        for (int q = 0; q < out_world; ++q) {
-                            uint8_t* dst = reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off;
-                            st_peer_word(dst + ((size_t)b * Nm + r0) * 8, v0, out_tag);
-                            st_peer_word(dst + ((size_t)b * Nm + r1) * 8, v1, out_tag);
+                        if constexpr (sizeof(T) == 2) {
+                            const uint32_t w2 = tp_pack2<T>(v0, v1);
+                            const size_t woff = out_off + ((((size_t)b * Nm + row0) >> 1) + g) * 8;
+                            for (int q = 0; q < out_world; ++q)
+                                st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + woff, w2, out_tag);
                         }
                     } else {
                         out[(size_t)b * Nm + r0] = DT<T>::from_f32(v0);
@@ -814,10 +855,22 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
             if (EXTRA && p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
-            if (out_world > 1) {
-                for (int q = 0; q < out_world; ++q)
-                    st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + out_off +
-                                     ((size_t)b * p.Nm[mm] + row) * 8, v, out_tag);
+            if (out_world > 1) {  // one word per row pair (row, row + 8): the thread of the lower row sums both
+                if constexpr (sizeof(T) == 2) {
+                    if (e & 8u) continue;
+                    float u = 0.f;
+                    for (uint32_t w = wa; w <= wz; ++w) {
+                        const uint32_t w_ua = w * wq + (w < wr ? w : wr);
+                        const uint32_t w_tl = p.by_upt.div(w_ua);
+                        u += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e + 8];
+                    }
+                    if (bias) u += DT<T>::to_f32(bias[row + 8]);
+                    if (p.vres[mm]) u += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row + 8]);
+                    const uint32_t w2 = tp_pack2<T>(v, u);
+                    const size_t woff = out_off + ((((size_t)b * p.Nm[mm] + (row & ~15u)) >> 1) + (row & 7u)) * 8;
+                    for (int q = 0; q < out_world; ++q)
+                        st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + woff, w2, out_tag);
+                }
             } else {
                 reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
             }

@@ -136,24 +136,24 @@ class RowParallelFP4Linear(_ShardedFP4Base):
 class PeerExchange:
     """Tensor-parallel exchange through peer (symmetric) memory, shared by all row-parallel layers of a model
     (include/fp4_b200.h: fp4_b200_tp_t).  A row-parallel layer PUSHES its partial output, as self-validating
-    64-bit words {fp32 value, tag32 = epoch}, into every rank's exchange buffer over NVLink (no fences, no flags,
-    no collective launch); the next column-parallel layer sums the ranks' partials (fp32, rank order) out of its
-    LOCAL buffer while it stages x.  Requires torch symmetric memory (NVLink peers of one box) and an initialised
-    process group."""
+    64-bit words {two 16-bit values, tag32 = epoch}, into every rank's exchange buffer over NVLink (no fences, no
+    flags, no collective launch); the next column-parallel layer sums the ranks' partials (fp32, rank order) out of
+    its LOCAL buffer while it stages x.  Requires torch symmetric memory (NVLink peers of one box), an initialised
+    process group and a 16-bit activation dtype."""
 
     def __init__(self, max_features: int, dtype: torch.dtype, device: torch.device, group=None, max_batch: int = 8):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
 
-        if dtype not in (torch.float16, torch.bfloat16, torch.float32):
-            raise ValueError("PeerExchange carries float16 / bfloat16 / float32 activations")
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("PeerExchange carries 16-bit activations")
         group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise ValueError("PeerExchange supports up to 8 ranks")
         self.dtype, self.device = dtype, device
-        self.slot_words = ((max_features * max_batch + 63) // 64) * 64       # one rank's region of one slot
-        self.slot_bytes = self.slot_words * 8                                # words are {fp32 value, tag32}
+        self.slot_words = ((max_features * max_batch // 2 + 63) // 64) * 64  # one rank's region of one slot
+        self.slot_bytes = self.slot_words * 8                                # a word: {two 16-bit values, tag32}
         self.buf = symm_mem.empty(2 * self.world * self.slot_words, dtype=torch.int64, device=device)
         self.buf.zero_()
         self._hbuf = symm_mem.rendezvous(self.buf, group=group)
