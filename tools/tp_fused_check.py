@@ -67,13 +67,13 @@ for _ in range(5):
     og = g(h0).float()
 ex.check()
 print(f"[rank {rank}] graph replay vs eager {((og - outs[0]).abs().max() / scale).item():.2e}", flush=True)
-# past 2^16 epochs (the 16-bit tags of round 1 came round again there): a batch-8 step, 11 000 batch-1 replays
-# (6 epochs each), then batch 8 again with the ranks out of step - words left by the first batch-8 step must not validate
+# past 2^16 epochs (the 16-bit tags of round 1 came round again there): a batch-8 step, 14 000 batch-1 replays
+# (5 epochs each), then batch 8 again with the ranks out of step - words left by the first batch-8 step must not validate
 with torch.no_grad():
     x8 = torch.randn(8, cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(77)).bfloat16()
     want8 = step_n(x8).float()
     step_p(x8)
-    for _ in range(11000):
+    for _ in range(14000):
         g(h0)
     if rank == 0:
         torch.cuda.synchronize()

@@ -226,6 +226,10 @@ __device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // written by othe
 // Four words (a, b: two each) of one rank's partial must carry `tag`; late words are re-read.  A peer that has not
 // delivered after kTpTimeoutNs (a dead rank, or call sequences that diverged) is fatal: the flag is raised for the
 // host and the kernel traps instead of computing with unvalidated words.
+#ifndef FP4_TP_FLY
+#define FP4_TP_FLY 4
+#endif
+constexpr int kTpFly = FP4_TP_FLY;  // ranks whose words a consumer thread loads before it looks at any of them
 constexpr unsigned long long kTpTimeoutNs = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void tp_wait4(const uint8_t* src, uint32_t tag, uint4& a, uint4& b, uint32_t* err) {
     unsigned long long t0 = 0;
@@ -459,17 +463,17 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                     for (int c = tid; c < nchunk; c += kThreads) {
                         const uint8_t* src = in_slot + ((size_t)b * (K >> 1) + (size_t)c * 4) * 8;
                         float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int r0 = 0; r0 < in_world; r0 += 4) {
-                            uint4 wa[4], wb[4];
+                        for (int r0 = 0; r0 < in_world; r0 += kTpFly) {
+                            uint4 wa[kTpFly], wb[kTpFly];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < kTpFly; ++j) {
                                 if (r0 + j < in_world) {
                                     wa[j] = ld_peer_u4(src + (size_t)(r0 + j) * p.tp.slot_bytes);
                                     wb[j] = ld_peer_u4(src + (size_t)(r0 + j) * p.tp.slot_bytes + 16);
                                 }
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {  // fixed rank order: every rank computes the same x
+                            for (int j = 0; j < kTpFly; ++j) {  // fixed rank order: every rank computes the same x
                                 if (r0 + j < in_world) {
                                     tp_wait4(src + (size_t)(r0 + j) * p.tp.slot_bytes, in_tag, wa[j], wb[j], p.tp.err);
                                     lo[0] += tp_lo<T>(wa[j].x); hi[0] += tp_hi<T>(wa[j].x);
@@ -836,18 +840,16 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                 v += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e];
             }
             const uint32_t b = e >> 4;
+            // lanes l and l + 8 of a 16-lane group hold the two halves of a pair (gate / up row, or rows r / r + 8 of
+            // an exchange word); the group shares tt, so all 16 lanes are here together
+            const uint32_t half_mask = (tid & 16u) ? 0xFFFF0000u : 0x0000FFFFu;
             if (gated) {  // e & 15 < 8: the gate partial sums; the up row's are 8 entries further
-                if (e & 8u) continue;
-                float u = 0.f;
-                for (uint32_t w = wa; w <= wz; ++w) {
-                    const uint32_t w_ua = w * wq + (w < wr ? w : wr);
-                    const uint32_t w_tl = p.by_upt.div(w_ua);
-                    u += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e + 8];
-                }
                 const uint32_t row = (tile0 + tt) * 8 + (e & 7);
-                if (p.vbias[0]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[0])[row]);
-                if (p.vbias[1]) u += DT<T>::to_f32(reinterpret_cast<const T*>(p.vbias[1])[row]);
-                reinterpret_cast<T*>(p.vout[0])[(size_t)b * p.Nm[0] + row] = DT<T>::from_f32(gate_act(v, gated_kind) * u);
+                const T* bias = reinterpret_cast<const T*>(p.vbias[(e >> 3) & 1u]);
+                if (bias) v += DT<T>::to_f32(bias[row]);
+                const float u = __shfl_down_sync(half_mask, v, 8);
+                if (!(e & 8u))
+                    reinterpret_cast<T*>(p.vout[0])[(size_t)b * p.Nm[0] + row] = DT<T>::from_f32(gate_act(v, gated_kind) * u);
                 continue;
             }
             const uint32_t row = (tile0 + tt) * 16 + (e & 15);
@@ -855,21 +857,15 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
             const T* bias = reinterpret_cast<const T*>(p.vbias[mm]);
             if (bias) v += DT<T>::to_f32(bias[row]);
             if (EXTRA && p.vres[mm]) v += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row]);
-            if (out_world > 1) {  // one word per row pair (row, row + 8): the thread of the lower row sums both
+            if (out_world > 1) {  // one word per row pair (row, row + 8), stored by the lane of the lower row
                 if constexpr (sizeof(T) == 2) {
-                    if (e & 8u) continue;
-                    float u = 0.f;
-                    for (uint32_t w = wa; w <= wz; ++w) {
-                        const uint32_t w_ua = w * wq + (w < wr ? w : wr);
-                        const uint32_t w_tl = p.by_upt.div(w_ua);
-                        u += sPart[((size_t)w * 2 + (tt == w_tl ? 0 : 1)) * per + e + 8];
+                    const float u = __shfl_down_sync(half_mask, v, 8);
+                    if (!(e & 8u)) {
+                        const uint32_t w2 = tp_pack2<T>(v, u);
+                        const size_t woff = out_off + ((((size_t)b * p.Nm[mm] + (row & ~15u)) >> 1) + (row & 7u)) * 8;
+                        for (int q = 0; q < out_world; ++q)
+                            st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + woff, w2, out_tag);
                     }
-                    if (bias) u += DT<T>::to_f32(bias[row + 8]);
-                    if (p.vres[mm]) u += DT<T>::to_f32(reinterpret_cast<const T*>(p.vres[mm])[(size_t)b * p.Nm[mm] + row + 8]);
-                    const uint32_t w2 = tp_pack2<T>(v, u);
-                    const size_t woff = out_off + ((((size_t)b * p.Nm[mm] + (row & ~15u)) >> 1) + (row & 7u)) * 8;
-                    for (int q = 0; q < out_world; ++q)
-                        st_peer_word(reinterpret_cast<uint8_t*>(p.tp.out_peer_base[q]) + woff, w2, out_tag);
                 }
             } else {
                 reinterpret_cast<T*>(p.vout[mm])[(size_t)b * p.Nm[mm] + row] = DT<T>::from_f32(v);
