@@ -24,6 +24,8 @@ def test_peer_exchange_two_ranks():
     for nccl, peer, rr in m:
         assert float(peer) <= 2e-2 and float(peer) <= 2.0 * float(nccl) + 1e-3 and float(rr) == 0.0
     assert out.count("ranks agree bit for bit: True") == 2
+    assert out.count("peer == all_gather + fp32 rank-order sum, bit for bit: True") == 2, out
+    assert out.count("bit-identical to the all_gather emulation: True") == 2, out
     skew = re.findall(r"skewed ranks, batch 1\.\.8: peer vs nccl worst ([0-9.e+-]+)", out)
     assert len(skew) == 2 and all(float(v) <= 3e-2 for v in skew), out
     assert len(re.findall(r"graph replay vs eager 0\.00e\+00", out)) == 2

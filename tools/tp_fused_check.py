@@ -39,7 +39,9 @@ with torch.no_grad():
         outs.append(step_p(h0).float().clone())
         say(f"peer step {i} done, state {ex.state.tolist()}")
     ex.check()
+    emu = bench.make_step_peer(tp_layers, ex, emulate=True)(h0).float()
 scale = ref_full.abs().max().item()
+print(f"[rank {rank}] peer == all_gather + fp32 rank-order sum, bit for bit: {torch.equal(emu, outs[0])}", flush=True)
 print(f"[rank {rank}] nccl vs full {((ref_nccl - ref_full).abs().max() / scale).item():.2e}  "
       f"peer vs full {((outs[0] - ref_full).abs().max() / scale).item():.2e}  "
       f"peer run-to-run {((outs[2] - outs[0]).abs().max() / scale).item():.2e}", flush=True)
@@ -52,6 +54,8 @@ import time  # noqa: E402
 worst = 0.0
 with torch.no_grad():
     step_n = bench.make_step(tp_layers, world)
+    step_e = bench.make_step_peer(tp_layers, ex, emulate=True)
+    exact = True
     for it, b in enumerate((1, 3, 2, 8, 1, 5)):
         xb = torch.randn(b, cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(40 + it)).bfloat16()
         if it % 2 == rank % 2:
@@ -60,7 +64,9 @@ with torch.no_grad():
         got = step_p(xb).float()
         want = step_n(xb).float()
         worst = max(worst, ((got - want).abs().max() / want.abs().max()).item())
+        exact = exact and torch.equal(got, step_e(xb).float())
     ex.check()
+print(f"[rank {rank}] skewed ranks, batch 1..8: bit-identical to the all_gather emulation: {exact}", flush=True)
 print(f"[rank {rank}] skewed ranks, batch 1..8: peer vs nccl worst {worst:.2e}", flush=True)
 g = GraphedCallable(step_p, [h0], warmup=3)
 for _ in range(5):

@@ -491,6 +491,10 @@ __global__ void __launch_bounds__(kThreads, FP4_STREAM_MINB) gemv_stream_kernel(
                             f[i] = odd ? got : lo[i];      // even lane: rows 0..3 its own, 4..7 the odd lane's low halves
                             f[i + 4] = odd ? hi[i] : got;  // odd lane: rows 8..11 the even lane's high halves, 12..15 its own
                         }
+                        // x = the all-reduced activation AS A TENSOR OF T would hold it (fp32 sum in rank order, rounded
+                        // once): bit-identical to gathering the partials and summing them on the host side
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = DT<T>::to_f32(DT<T>::from_f32(f[i]));
                         stage_chunk(b, c, f);
                     }
                 }
