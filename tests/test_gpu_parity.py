@@ -654,3 +654,59 @@ def test_full_size_dequant_checksum_and_gemv_linearity(cuda):
     assert normwise((y1 + 2 * y2).cpu().numpy(), y12.cpu().numpy()) <= 1e-5
     W = ext.dequantize_fp4(A, am, 64, N, K, ext.float32).double()
     assert normwise(y1.cpu().numpy(), (x1.double() @ W.t()).cpu().numpy()) <= 1e-5
+
+
+# ---------------------------------------------------------------- guard bands: no kernel writes outside its output
+def _guarded(n_elems, dtype, dev, band=4096):
+    """An output of n_elems inside a sentinel-filled allocation (band elements either side, 256-byte aligned)."""
+    buf = torch.full((n_elems + 2 * band,), -7.0, dtype=dtype, device=dev)
+    return buf, buf[band:band + n_elems], band
+
+
+def _bands_intact(buf, band, n_elems):
+    return bool((buf[:band] == -7.0).all().item() and (buf[band + n_elems:] == -7.0).all().item())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_kernels_stay_inside_their_outputs(cuda, dtype):
+    """compute-sanitizer is closed on the GPU pool; this is the out-of-bounds check that can run: every kernel family
+    of the path (dequant tree / codebook, GEMV streaming / split / generic, grouped, tcgen05 GEMM) writes into an
+    output surrounded by sentinel bands, called through the raw C-ABI with ragged and aligned sizes."""
+    L = _lib.lib
+    dcode = {torch.float16: 0, torch.float32: 1, torch.bfloat16: 2}[dtype]
+    st = torch.cuda.current_stream(cuda).cuda_stream
+    code = _code(cuda)
+    for n in (64 * 33 + 7, 4096 * 64, 17):  # dequant
+        packed, absmax = synth_bytes(n, 64, seed=n % 89)
+        A, am = to_dev(packed, cuda), to_dev(absmax, cuda)
+        for cd in (None, code.data_ptr()):
+            buf, out, band = _guarded(n, dtype, cuda)
+            _lib.check(L.fp4_b200_dequantize(A.data_ptr(), am.data_ptr(), cd, out.data_ptr(), n, 64, dcode, st), "dequant")
+            torch.cuda.synchronize()
+            assert _bands_intact(buf, band, n), ("dequant", n, cd is None)
+            assert not bool((out == -7.0).any().item())
+    shapes = [(4096, 4096, 1), (1024, 4096, 3), (14336, 4096, 8), (48, 256, 5), (1000, 320, 2), (4096, 14336, 8),
+              (24, 192, 1)]
+    for N, K, batch in shapes:  # GEMV: streaming, two-launch split, generic
+        packed, absmax = synth_bytes(N * K, 64, seed=(N + K) % 83)
+        A, am = to_dev(packed, cuda), to_dev(absmax, cuda)
+        x = torch.randn(batch, K, device=cuda).to(dtype)
+        for flags in (1, 1 | 2):
+            buf, out, band = _guarded(batch * N, dtype, cuda)
+            _lib.check(L.fp4_b200_gemv(x.data_ptr(), A.data_ptr(), am.data_ptr(), None, code.data_ptr(), None,
+                                       out.data_ptr(), batch, N, K, 64, dcode, flags, None, 0, st), "gemv")
+            torch.cuda.synchronize()
+            assert _bands_intact(buf, band, batch * N), ("gemv", N, K, batch, flags)
+            assert not bool((out == -7.0).any().item()), ("gemv wrote everything", N, K, batch, flags)
+    if dtype != torch.float32:  # tcgen05 GEMM (ragged M, N not a tile multiple)
+        import ctypes
+        for M, N, K in ((37, 1000, 320), (300, 4096, 4096), (1111, 1032, 512)):
+            packed, absmax = synth_bytes(N * K, 64, seed=(M + N) % 79)
+            A, am = to_dev(packed, cuda), to_dev(absmax, cuda)
+            x = torch.randn(M, K, device=cuda).to(dtype)
+            buf, out, band = _guarded(M * N, dtype, cuda)
+            _lib.check(L.fp4_b200_gemm(x.data_ptr(), A.data_ptr(), am.data_ptr(), code.data_ptr(), None, out.data_ptr(),
+                                       M, N, K, 64, dcode, 1, None, ctypes.c_size_t(0), st), "gemm")
+            torch.cuda.synchronize()
+            assert _bands_intact(buf, band, M * N), ("gemm", M, N, K)
+            assert not bool((out == -7.0).any().item()), ("gemm wrote everything", M, N, K)
