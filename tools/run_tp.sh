@@ -1,4 +1,4 @@
-# usage: run_tp.sh N [workload]
+# usage: run_tp.sh N [workload]   (gpurun --gpus N: the tensor-parallel bench line, summary printed; N=2 also runs tests/test_gpu_tp.py)
 N=$1; WL=${2:-mistral7b}
 if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_gpu_tp.py -q -m gpu 2>&1 | tail -5; fi
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 30 --warmup 5 --workload $WL > gpurun_out/r02_bench_tp${N}_${WL}.json 2> gpurun_out/r02_bench_tp${N}_${WL}.err
