@@ -118,3 +118,15 @@ def test_codebook_identity_accepts_either_sign_of_zero():
     other[4] = 0.333333  # the reference's CODE_PARAM quirk: a different table, generic kernel
     assert not ext.code_is_bnb_fp4(other)
     assert not ext.code_is_bnb_fp4(ref[:8].clone())
+
+
+def test_prefill_dispatch_rule_follows_the_measured_sweep():
+    """profiles/r02_gemm_sweep_shapes*.log: which of the two bit-identical prefill paths the dispatcher picks."""
+    from torch_bnb_fp4_b200 import _fused_gemm_wins as wins
+    # (rows, out_features, in_features) -> fused GEMM faster than dequant + cuBLAS on the B200
+    assert wins(16, 4096, 4096) and wins(128, 1024, 4096) and wins(64, 8192, 8192) and wins(128, 28672, 8192)
+    assert wins(256, 14336, 4096) and wins(512, 8192, 8192) and wins(512, 28672, 8192) and wins(256, 28672, 4096)
+    assert not wins(256, 4096, 4096) and not wins(512, 1024, 4096)          # few row tiles: 0.9x
+    assert not wins(16, 4096, 14336) and not wins(512, 4096, 14336)          # few row tiles x long K: 0.6x
+    assert wins(64, 28672, 14336)                                            # a full wave of row tiles
+    assert not wins(513, 28672, 8192) and not wins(4096, 28672, 8192)        # cuBLAS wins beyond 512 rows

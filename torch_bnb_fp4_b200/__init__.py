@@ -36,10 +36,30 @@ from .ext import ScalarType as ScalarType_
 T_Model = TypeVar("T_Model", bound=nn.Module)
 
 GEMV_MAX_BATCH = 8      # rows of x handled by the fused dequant-GEMV
-GEMV_X_SMEM_BYTES = 150 * 1024  # x terms the streaming GEMV can stage next to one ring slot per warp
 GEMV_TWICE_MAX_WEIGHTS = 32 * 1024 * 1024  # 9..16 rows: layers up to this many weights take two 8-row GEMVs
 GEMM_MIN_ROWS = 9       # rows of x from which the dequant-fused tcgen05 GEMM is used
-GEMM_MAX_ROWS = 512     # ... and up to which it beats new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
+GEMM_MAX_ROWS = 512     # ... and up to which it can beat new-dequant + cuBLAS on B200 (profiles/r01_gemm_sweep_*.log)
+GEMM_SMALL_ROWS = 128   # up to here the fused GEMM wins (or ties) on every layer shape with K <= GEMM_LONG_K
+GEMM_MID_MIN_WEIGHTS = 48 * 1024 * 1024  # 129..512 rows: only layers with at least this many weights
+GEMM_LONG_K = 8192      # beyond this K a weight tile is a long serial k loop: the fused GEMM needs a full wave of them
+GEMM_LONG_K_MIN_OUT = 148 * 128
+
+
+def _fused_gemm_wins(rows: int, out_features: int, in_features: int) -> bool:
+    """Which of the two bit-identical prefill paths is faster on a B200 (profiles/r02_gemm_sweep_shapes.log,
+    r02_gemm_sweep_shapes_small_m.log, the gemm_sweep key of the bench line): the fused kernel runs one CTA per 128
+    weight rows, so a layer with few row tiles (4096x4096: 32) leaves most SMs idle and a long K makes each tile a
+    long serial loop (4096x14336: 0.6x at every M), while dequant + cuBLAS pays a full dequant pass that only large
+    layers amortise.  Measured speed-up of the fused kernel: 1.0-1.8x for M <= 128 with K <= 8192 on every shape;
+    for 256-512 rows 1.0-1.6x on 8192x8192 / 14336x4096 / 28672x8192 and 0.9x on 4096x4096 / 1024x4096; <= 1.03x
+    beyond 512 rows everywhere."""
+    if rows > GEMM_MAX_ROWS:
+        return False
+    if in_features > GEMM_LONG_K and out_features < GEMM_LONG_K_MIN_OUT:
+        return False
+    if rows <= GEMM_SMALL_ROWS:
+        return True
+    return out_features * in_features >= GEMM_MID_MIN_WEIGHTS
 
 
 class ScalarType(Enum):
@@ -240,17 +260,12 @@ class QuantData:
         gemm_ok = (self.nested is None and self._code_is_std
                    and _ext.gemm_fp4_supported(rows, self.M, self.N, self.blocksize, A.dtype))
         if rows <= GEMV_MAX_BATCH and k % 32 == 0 and self.blocksize % 32 == 0:
-            # the streaming GEMV keeps x (as integer terms) in shared memory: rows * K * 2 bytes for 16-bit
-            # inputs.  Where that does not fit (e.g. 8 rows x K = 14336) the tensor-core GEMM with a 16-token tile
-            # is several times faster than the stream-K fallback
-            # (fp32 inputs take four integer terms per element instead of two and have no fused GEMM: the C-ABI then
-            # runs the GEMV as two launches of half the rows each)
-            x_bytes = rows * k * (4 if A.dtype == torch.float32 else 2)
-            too_big = rows > 2 and x_bytes > GEMV_X_SMEM_BYTES
-            if not (too_big and gemm_ok):
-                if not A.is_contiguous():
-                    A = A.contiguous()
-                return self._qgemv(A)
+            # the streaming GEMV keeps x (as integer terms) in shared memory; where a batch does not fit (8 rows x
+            # K = 14336, fp32 5..8 rows x K = 8192) the C-ABI runs it as two launches of half the rows each - still
+            # 2-3x faster than the tensor-core GEMM with a 16-token tile (88 us on 4096x14336)
+            if not A.is_contiguous():
+                A = A.contiguous()
+            return self._qgemv(A)
         if (GEMV_MAX_BATCH < rows <= 2 * GEMV_MAX_BATCH and self.numel <= GEMV_TWICE_MAX_WEIGHTS
                 and k % 32 == 0 and self.blocksize % 32 == 0 and self._code_is_std):
             # 9..16 rows on a small layer: the GEMM's few weight tiles leave most SMs idle and its one dequantiser
@@ -264,7 +279,7 @@ class QuantData:
             else:
                 y = torch.cat([self._qgemv(A2[:GEMV_MAX_BATCH]), self._qgemv(A2[GEMV_MAX_BATCH:])], dim=0)
             return y.view(A.shape[:-1] + (self.M,))
-        if rows <= GEMM_MAX_ROWS and gemm_ok:
+        if gemm_ok and _fused_gemm_wins(rows, self.M, self.N):
             if not A.is_contiguous():
                 A = A.contiguous()
             return self._qgemm(A)
